@@ -1,0 +1,457 @@
+// mg_gemm.cu — the tcgen05/TMEM/TMA tensor-core engine.
+//
+// Replaces the reference's fp64 cuBLAS products on the statistics path
+//   src/adapters/LlamaAdapter.py:115-147  (H^T H, per-head bmm, X^T X)
+// and supplies the bf16-split fp32-accurate GEMM the blocked Cholesky / TRSM / Nystrom kernels use.
+//
+// Kernel shape (one CTA per SM, persistent over work items):
+//   warp 0      : TMA producer   — 64-column x BK-row boxes, SWIZZLE_128B, 3D maps (col,row,plane)
+//   warp 1      : MMA issuer     — tcgen05.mma 128 x BN x 16, both operands MN-major, fp32 in TMEM
+//   warps 2..5  : epilogue       — tcgen05.ld 32x32b, fused accumulate / triangular predication
+// TMEM holds two accumulators (2 x BN columns) so the epilogue of tile i overlaps tile i+1.
+#include "mg_gemm.cuh"
+
+#include <cuda.h>
+
+#include <mutex>
+
+#include "mg_ptx.cuh"
+
+namespace mg {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kChunkCols = 64;                    // one TMA box = 64 bf16 = 128 B wide
+constexpr uint32_t kBoxBytes = BK * 128;          // 8 KB
+constexpr uint32_t kABytes = (BM / 64) * kBoxBytes;  // 16 KB
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t b_bytes = (BN / 64) * kBoxBytes;
+  static constexpr uint32_t stage_bytes = kABytes + b_bytes;
+  static constexpr int stages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 + 512;
+};
+
+struct KParams {
+  int64_t M, N, K;
+  float* D;
+  int64_t ldd;
+  float alpha;
+  int tiles, epi, hd;
+  int ksplit, kb_per_split, kblocks;
+  int MT, NT, ntiles, total_work;
+  int npairs;
+  int pair_a[kMaxPairs];
+  int pair_b[kMaxPairs];
+  int atomic;
+  int vec_ok;  // D and ldd allow float4 accesses
+};
+
+struct Work {
+  int mi, nj, kb0, kb1;
+};
+
+template <int BN>
+__device__ __forceinline__ Work decode_work(const KParams& p, int w) {
+  constexpr int R = BN / BM;
+  const int tile = w / p.ksplit;
+  const int ks = w - tile * p.ksplit;
+  Work o;
+  if (p.tiles == TILES_FULL) {
+    o.nj = tile / p.MT;
+    o.mi = tile - o.nj * p.MT;
+  } else if (p.tiles == TILES_DIAG) {
+    o.mi = tile;
+    o.nj = tile;
+  } else {
+    // column nj of the tile grid owns rows mi in [0, min(R*(nj+1), MT)); only the last column can
+    // be clipped, so prefix(nj) = R*nj*(nj+1)/2 for every valid nj.
+    int nj = static_cast<int>((sqrtf(1.f + 8.f * static_cast<float>(tile) / R) - 1.f) * 0.5f);
+    if (nj >= p.NT) nj = p.NT - 1;
+    while (nj > 0 && R * nj * (nj + 1) / 2 > tile) --nj;
+    while (nj + 1 < p.NT && R * (nj + 1) * (nj + 2) / 2 <= tile) ++nj;
+    o.nj = nj;
+    o.mi = tile - R * nj * (nj + 1) / 2;
+  }
+  o.kb0 = ks * p.kb_per_split;
+  o.kb1 = min(p.kblocks, o.kb0 + p.kb_per_split);
+  return o;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const KParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
+  uint64_t* empty = full + C::stages;
+  uint64_t* tmem_full = empty + C::stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const Work wk = decode_work<BN>(p, w);
+        const int a_col = wk.mi * BM;
+        const int b_col = wk.nj * BN;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          for (int pr = 0; pr < p.npairs; ++pr) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_expect_tx(&full[stage], C::stage_bytes);
+            uint8_t* sa = smem + stage * C::stage_bytes;
+            uint8_t* sb = sa + kABytes;
+#pragma unroll
+            for (int c = 0; c < BM / kChunkCols; ++c)
+              tma_load_3d(sa + c * kBoxBytes, &tmA, &full[stage], a_col + c * kChunkCols, kb * BK,
+                          p.pair_a[pr]);
+#pragma unroll
+            for (int c = 0; c < BN / kChunkCols; ++c)
+              tma_load_3d(sb + c * kBoxBytes, &tmB, &full[stage], b_col + c * kChunkCols, kb * BK,
+                          p.pair_b[pr]);
+            if (++stage == C::stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+        const Work wk = decode_work<BN>(p, w);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        uint32_t accum = 0;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          for (int pr = 0; pr < p.npairs; ++pr) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
+            const uint32_t sb = sa + kABytes;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+              accum = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == C::stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row_in_tile = q * 32 + lane;
+    int it = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+      const Work wk = decode_work<BN>(p, w);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int64_t gr = static_cast<int64_t>(wk.mi) * BM + row_in_tile;
+      const int64_t warp_row0 = static_cast<int64_t>(wk.mi) * BM + q * 32;
+      const bool row_ok = gr < p.M;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
+        // warp-uniform skips: chunk entirely out of range / strictly below the diagonal /
+        // outside this warp's head block.
+        if (gc0 >= p.N) break;
+        if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
+        if (p.tiles == TILES_DIAG && p.hd < 128) {
+          const int64_t hb0 = (warp_row0 / p.hd) * p.hd;  // 32 | hd so a warp sits in one head
+          if (gc0 + 31 < hb0 || gc0 >= hb0 + p.hd) continue;
+        }
+        float v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(as * BN + cc * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float* dst;
+        bool full_chunk;
+        if (p.tiles == TILES_DIAG) {
+          const int64_t head = gr / p.hd;
+          const int64_t hb0 = head * p.hd;
+          dst = p.D + head * p.hd * p.hd + (gr - hb0) * p.hd + (gc0 - hb0);
+          full_chunk = (gc0 >= hb0) && (gc0 + 32 <= hb0 + p.hd) && (gc0 + 32 <= p.N);
+          if (!full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t gc = gc0 + j;
+              if (gc >= hb0 && gc < hb0 + p.hd && gc < p.N) {
+                const float x = p.alpha * v[j];
+                if (p.epi == EPI_STORE) dst[j] = x;
+                else if (p.atomic) atomicAdd(dst + j, x);
+                else dst[j] += x;
+              }
+            }
+            continue;
+          }
+        } else {
+          dst = p.D + gr * p.ldd + gc0;
+          full_chunk = (gc0 + 32 <= p.N) && (p.tiles != TILES_UPPER || gc0 >= gr);
+          if (!full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t gc = gc0 + j;
+              if (gc < p.N && (p.tiles != TILES_UPPER || gc >= gr)) {
+                const float x = p.alpha * v[j];
+                if (p.epi == EPI_STORE) dst[j] = x;
+                else if (p.atomic) atomicAdd(dst + j, x);
+                else dst[j] += x;
+              }
+            }
+            continue;
+          }
+        }
+        // full 32-wide chunk
+        if (p.atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, p.alpha * v[j]);
+        } else if (p.vec_ok) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          if (p.epi == EPI_STORE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              d4[j] = make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1],
+                                  p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
+          } else {
+            float4 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = d4[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j].x += p.alpha * v[4 * j];
+              o[j].y += p.alpha * v[4 * j + 1];
+              o[j].z += p.alpha * v[4 * j + 2];
+              o[j].w += p.alpha * v[4 * j + 3];
+              d4[j] = o[j];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = p.alpha * v[j];
+            if (p.epi == EPI_STORE) dst[j] = x;
+            else dst[j] += x;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 3D map over bf16 planes: dim0 = columns (contiguous), dim1 = rows (K), dim2 = plane.
+int make_plane_map(CUtensorMap* tm, const __nv_bfloat16* base, int64_t cols, int64_t rows,
+                   int64_t ld, int planes, int64_t plane_stride) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -90;
+  if (planes < 1) return -91;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) || ld < cols) return -92;
+  if (planes > 1 && (plane_stride % 8)) return -93;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(planes)};
+  const int64_t ps = planes > 1 ? plane_stride : rows * ld;
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ps) * 2};
+  cuuint32_t box[3] = {kChunkCols, BK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(static_cast<const void*>(base)), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -94;
+}
+
+template <int BN>
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp,
+                cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes);
+    if (e != cudaSuccess) return -1000 - static_cast<int>(e);
+    attr_set = true;
+  }
+  const int grid = kp.total_work < device_sm_count() ? kp.total_work : device_sm_count();
+  gemm_tn_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, kp);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
+}
+
+}  // namespace
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
+  if (!a.A || !a.B || !a.D) return -1;
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return -2;
+  if (a.npairs < 1 || a.npairs > kMaxPairs) return -3;
+  for (int i = 0; i < a.npairs; ++i)
+    if (a.pair_a[i] < 0 || a.pair_a[i] >= a.a_planes || a.pair_b[i] < 0 ||
+        a.pair_b[i] >= a.b_planes)
+      return -4;
+  if (a.tiles == TILES_UPPER && a.M != a.N) return -5;
+  if (a.tiles == TILES_DIAG) {
+    if (a.M != a.N) return -5;
+    if (a.hd != 32 && a.hd != 64 && a.hd != 128) return -6;
+    if (a.M % a.hd) return -6;
+  } else if (a.ldd < a.N) {
+    return -7;
+  }
+  if (a.epi != EPI_STORE && a.epi != EPI_ADD) return -8;
+
+  const bool bn256 = (a.tiles != TILES_DIAG) && a.N > 128;
+  const int BN = bn256 ? 256 : 128;
+
+  KParams kp{};
+  kp.M = a.M;
+  kp.N = a.N;
+  kp.K = a.K;
+  kp.D = a.D;
+  kp.ldd = a.ldd;
+  kp.alpha = a.alpha;
+  kp.tiles = a.tiles;
+  kp.epi = a.epi;
+  kp.hd = a.hd > 0 ? a.hd : 128;
+  kp.npairs = a.npairs;
+  for (int i = 0; i < a.npairs; ++i) {
+    kp.pair_a[i] = a.pair_a[i];
+    kp.pair_b[i] = a.pair_b[i];
+  }
+  kp.MT = static_cast<int>((a.M + BM - 1) / BM);
+  kp.NT = static_cast<int>((a.N + BN - 1) / BN);
+  if (a.tiles == TILES_FULL) {
+    kp.ntiles = kp.MT * kp.NT;
+  } else if (a.tiles == TILES_DIAG) {
+    kp.ntiles = kp.MT;
+  } else {
+    const int R = BN / BM;
+    const int last = (R * kp.NT < kp.MT) ? R * kp.NT : kp.MT;
+    kp.ntiles = R * (kp.NT - 1) * kp.NT / 2 + last;
+  }
+  kp.kblocks = static_cast<int>((a.K + BK - 1) / BK);
+  int ksplit = a.ksplit;
+  if (ksplit <= 0) {
+    ksplit = 1;
+    if (a.epi == EPI_ADD && kp.ntiles < device_sm_count()) {
+      ksplit = (2 * device_sm_count() + kp.ntiles - 1) / kp.ntiles;
+      // keep at least 8 k-blocks per split so the pipeline fill is amortised
+      const int max_split = (kp.kblocks + 7) / 8;
+      if (ksplit > max_split) ksplit = max_split;
+      if (ksplit < 1) ksplit = 1;
+    }
+  }
+  if (ksplit > 1 && a.epi != EPI_ADD) return -9;
+  if (ksplit > kp.kblocks) ksplit = kp.kblocks;
+  kp.kb_per_split = (kp.kblocks + ksplit - 1) / ksplit;
+  kp.ksplit = (kp.kblocks + kp.kb_per_split - 1) / kp.kb_per_split;
+  kp.atomic = kp.ksplit > 1;
+  kp.total_work = kp.ntiles * kp.ksplit;
+  kp.vec_ok = ((reinterpret_cast<uintptr_t>(a.D) & 15) == 0) &&
+              (a.tiles == TILES_DIAG ? (kp.hd % 4 == 0) : (a.ldd % 4 == 0));
+
+  CUtensorMap tmA, tmB;
+  int rc = make_plane_map(&tmA, a.A, a.M, a.K, a.lda, a.a_planes, a.a_plane_stride);
+  if (rc) return rc;
+  rc = make_plane_map(&tmB, a.B, a.N, a.K, a.ldb, a.b_planes, a.b_plane_stride);
+  if (rc) return rc;
+  return bn256 ? launch_impl<256>(tmA, tmB, kp, stream) : launch_impl<128>(tmA, tmB, kp, stream);
+}
+
+}  // namespace mg

@@ -1,0 +1,56 @@
+// mg_gemm.cuh — internal interface of the tensor-core engine (mg_gemm.cu).
+//
+// One persistent, warp-specialised tcgen05 kernel computes
+//     D[M,N] (op)= alpha * sum_p sum_k A_{pa(p)}[k, m] * B_{pb(p)}[k, n]
+// where A and B are row-major bf16 "planes" of shape [K, M] / [K, N] (both operands MN-major:
+// the reduction index is the slow one, exactly the layout of an activation matrix X[T, n] in
+// C = X^T X and of a Cholesky block row U12[nb, n]).  Planes let an fp32 matrix be fed as its
+// bf16 hi/mid/lo split so tensor-core products reach fp32 accuracy.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mg {
+
+enum TileSet : int {
+  TILES_FULL = 0,   // every 128 x BN tile of D
+  TILES_UPPER = 1,  // only tiles that intersect col >= row (M == N); elements col < row untouched
+  TILES_DIAG = 2,   // 128 x 128 diagonal tiles; D is [M/hd, hd, hd] packed per-head blocks
+};
+
+enum EpiOp : int {
+  EPI_STORE = 0,  // D  = alpha * acc
+  EPI_ADD = 1,    // D += alpha * acc   (atomic when ksplit > 1)
+};
+
+constexpr int kMaxPairs = 8;
+
+struct GemmArgs {
+  const __nv_bfloat16* A;  // plane 0 of A, [K, M] row-major
+  int64_t lda;             // elements
+  int64_t a_plane_stride;  // elements between planes (0 if a single plane)
+  int a_planes;
+  const __nv_bfloat16* B;
+  int64_t ldb;
+  int64_t b_plane_stride;
+  int b_planes;
+  int npairs;  // >= 1
+  int pair_a[kMaxPairs];
+  int pair_b[kMaxPairs];
+  int64_t M, N, K;
+  float* D;
+  int64_t ldd;
+  float alpha;
+  int tiles;   // TileSet
+  int epi;     // EpiOp
+  int hd;      // TILES_DIAG: block size (divides 128)
+  int ksplit;  // >= 1; > 1 requires EPI_ADD (atomics); 0 = choose automatically
+};
+
+// Returns 0, a negative argument error, or -1000 - cudaError_t.
+int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace mg
