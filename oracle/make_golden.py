@@ -1,0 +1,288 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+The reference hard-codes "cuda" device strings (src/model_utils.py:26-31 and literals in the
+hooks / compress_* functions), so a test-only shim maps every cuda device request to "cpu" before
+the reference modules are imported.  Nothing from the reference is copied: its functions are
+called and their inputs / outputs recorded.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = Path(os.environ.get("MODEGPT_REFERENCE", "/root/reference"))
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+# ---------------------------------------------------------------------------------- cpu shim
+def install_cpu_shim() -> None:
+    def fix(dev):
+        if isinstance(dev, (str, torch.device)) and str(dev).startswith("cuda"):
+            return "cpu"
+        return dev
+
+    orig_to = torch.Tensor.to
+
+    def to(self, *args, **kw):
+        args = tuple(fix(a) for a in args)
+        if "device" in kw:
+            kw["device"] = fix(kw["device"])
+        return orig_to(self, *args, **kw)
+
+    torch.Tensor.to = to
+    for name in ("zeros", "tensor", "eye", "empty", "ones", "load"):
+        orig = getattr(torch, name)
+
+        def wrap(*a, __orig=orig, **kw):
+            if "device" in kw:
+                kw["device"] = fix(kw["device"])
+            if "map_location" in kw:
+                kw["map_location"] = fix(kw["map_location"])
+            return __orig(*a, **kw)
+
+        setattr(torch, name, wrap)
+    orig_lin = nn.Linear.__init__
+
+    def lin_init(self, *a, **kw):
+        if "device" in kw:
+            kw["device"] = fix(kw["device"])
+        return orig_lin(self, *a, **kw)
+
+    nn.Linear.__init__ = lin_init
+
+
+def f64(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to(torch.float64).cpu().numpy()
+
+
+def shaped_gram(rng: np.random.Generator, t: int, n: int, spread: float = 1.0):
+    """Activations with a per-channel scale spread so score gaps sit far above rounding noise."""
+    x = rng.standard_normal((t, n)) * np.exp(spread * rng.standard_normal(n))
+    mix = np.eye(n) + 0.15 * rng.standard_normal((n, n)) / np.sqrt(n)
+    x = x @ mix
+    return x, x.T @ x / t
+
+
+# ---------------------------------------------------------------------------------- pieces
+def golden_utils(ref, rng):
+    out = {}
+    m = shaped_gram(rng, 200, 24)[1]
+    out["sqrt_in"] = m
+    out["sqrt_ridge"] = np.array(1e-4)
+    out["sqrt_out"] = f64(ref.cu.sqrt_M(torch.tensor(m), ridge_lambda=1e-4))
+    s, si = ref.cu.sqrt_M(torch.tensor(m), ridge_lambda=1e-2, inverse_sqrt=True)
+    out["sqrt2_out"], out["sqrt2_inv"] = f64(s), f64(si)
+    cases = [
+        (rng.uniform(0.05, 0.6, 12), 0.30, 0.04948, 0.95),
+        (rng.uniform(0.05, 0.6, 32), 0.25, 0.04948, 0.95),
+        (np.array([0.01, 0.5, 0.6, 0.7, 0.02, 0.8]), 0.5, 0.15, 0.8),    # cap + redistribution
+        # (the reference loop re-opens capped layers every round; strongly skewed weights make it
+        #  converge only after ~1e4+ rounds, so the fixtures stay with cases that terminate fast)
+        (rng.uniform(0.2, 0.3, 8), 0.4, 0.15, 0.8),
+    ]
+    for i, (bi, ratio, smooth, cap) in enumerate(cases):
+        keep = ref.cu.allocate_global_sparsity(list(map(float, bi)), compression_ratio=ratio,
+                                               smoothing=smooth, max_sparsity=cap)
+        out[f"alloc{i}_bi"] = bi
+        out[f"alloc{i}_params"] = np.array([ratio, smooth, cap])
+        out[f"alloc{i}_keep"] = np.array(keep)
+    np.savez_compressed(OUT / "utils.npz", **out)
+
+
+def golden_mlp(ref, rng):
+    out = {}
+    for tag, (n, d, keep, ridge) in {"a": (96, 40, 0.75, 1e-2), "b": (160, 64, 0.6, 1e-4)}.items():
+        _, c = shaped_gram(rng, 4 * n, n)
+        wu = torch.tensor(rng.standard_normal((n, d)) * 0.05).to(torch.bfloat16)
+        wg = torch.tensor(rng.standard_normal((n, d)) * 0.05).to(torch.bfloat16)
+        wd = torch.tensor(rng.standard_normal((d, n)) * 0.05).to(torch.bfloat16)
+        comps = ref.ma.MLPComponents(block=None, up_proj=types.SimpleNamespace(weight=wu),
+                                     down_proj=types.SimpleNamespace(weight=wd),
+                                     gate_proj=types.SimpleNamespace(weight=wg))
+        scores = ref.mlp.get_ridge_scores(torch.tensor(c), layer_idx=0, ridge_lambda=ridge)
+        up_t, down_t, gate_t, rank = ref.mlp.compress_weights(comps, torch.tensor(c), keep, 0, ridge)
+        out[f"{tag}_c"] = c
+        out[f"{tag}_wu"], out[f"{tag}_wg"], out[f"{tag}_wd"] = f64(wu), f64(wg), f64(wd)
+        out[f"{tag}_params"] = np.array([keep, ridge])
+        out[f"{tag}_scores"] = f64(scores)
+        # compress_nystrom saves the transposes (compress_mlp.py:97)
+        out[f"{tag}_up"], out[f"{tag}_gate"], out[f"{tag}_down"] = f64(up_t.T), f64(gate_t.T), f64(down_t.T)
+        out[f"{tag}_rank"] = np.array(rank)
+    np.savez_compressed(OUT / "mlp.npz", **out)
+
+
+def golden_qk(ref, rng):
+    out = {}
+    hd, d = 32, 48
+    # GQA group of 3 query heads per kv head
+    cq = np.stack([shaped_gram(rng, 300, hd)[1] for _ in range(3)])
+    ck = shaped_gram(rng, 300, hd)[1]
+    wq = torch.tensor(rng.standard_normal((3, hd, d))).to(torch.bfloat16)
+    wk = torch.tensor(rng.standard_normal((1, hd, d))).to(torch.bfloat16)
+    qo, ko, masks = [], [], []
+    ref.qk.compress_head_llama_grouped(0, 3, torch.tensor(cq), torch.tensor(ck)[None], wq, wk, qo, ko,
+                                       masks, rank=20, ridge_lambda=1e-2)
+    out.update(gqa_cq=cq, gqa_ck=ck, gqa_wq=f64(wq), gqa_wk=f64(wk), gqa_rank=np.array(20),
+               gqa_ridge=np.array(1e-2), gqa_mask=masks[0].numpy(),
+               gqa_q=np.stack([f64(x) for x in qo]), gqa_k=f64(ko[0]))
+    # MHA llama
+    cq1, ck1 = shaped_gram(rng, 300, hd)[1], shaped_gram(rng, 300, hd)[1]
+    qo, ko, masks = [], [], []
+    ref.qk.compress_head_llama(torch.tensor(cq1), torch.tensor(ck1), wq[0], wk[0], qo, ko, masks, rank=18)
+    out.update(mha_cq=cq1, mha_ck=ck1, mha_rank=np.array(18), mha_mask=masks[0].numpy(),
+               mha_q=f64(qo[0]), mha_k=f64(ko[0]))
+    # OPT
+    bq, bk = torch.tensor(rng.standard_normal(hd)), torch.tensor(rng.standard_normal(hd))
+    qo, ko, bqo, bko = [], [], [], []
+    ref.qk.compress_head_opt(torch.tensor(cq1), torch.tensor(ck1), wq[1], wk[0], bq, bk, qo, ko, bqo,
+                             bko, rank=11)
+    out.update(opt_rank=np.array(11), opt_wq=f64(wq[1]), opt_bq=f64(bq), opt_bk=f64(bk),
+               opt_q=f64(qo[0]), opt_k=f64(ko[0]), opt_bq_out=f64(bqo[0]), opt_bk_out=f64(bko[0]))
+    np.savez_compressed(OUT / "qk.npz", **out)
+
+
+def golden_vo(ref, rng):
+    out = {}
+    d, hd, rank = 48, 16, 10
+    _, c = shaped_gram(rng, 400, d, spread=0.7)
+    root = ref.cu.sqrt_M(torch.tensor(c), ridge_lambda=1e-5)
+    root_inv = torch.linalg.inv(root)
+    # MHA: 2 heads
+    wv = torch.tensor(rng.standard_normal((2 * hd, d)) * 0.1).to(torch.bfloat16)
+    wo = torch.tensor(rng.standard_normal((d, 2 * hd)) * 0.1).to(torch.bfloat16)
+    vs, os_ = [], []
+    for h in range(2):
+        ref.vo.compress_head(h, hd, rank, wv, wo, root, root_inv, vs, os_)
+    out.update(c=c, ridge=np.array(1e-5), rank=np.array(rank), hd=np.array(hd),
+               mha_wv=f64(wv), mha_wo=f64(wo), mha_v=np.concatenate([f64(x) for x in vs], 0),
+               mha_o=np.concatenate([f64(x) for x in os_], 1))
+    # GQA: 1 kv head serving 2 query heads
+    wv1 = wv[:hd]
+    vs, os_ = [], []
+    ref.vo.compress_head_grouped(0, 2, hd, rank, wv1, wo, root, root_inv, vs, os_)
+    out.update(gqa_wv=f64(wv1), gqa_v=f64(vs[0]), gqa_o=np.concatenate([f64(x) for x in os_], 1))
+    np.savez_compressed(OUT / "vo.npz", **out)
+
+
+def golden_pipeline(ref, tag: str, n_kv: int, qwen: bool = False):
+    """Whole reference pipeline (calibration -> allocation -> type I/II/III) on a tiny random-init
+    model, recording the hook inputs so kernels can be checked on identical activations."""
+    from transformers import AutoModelForCausalLM, LlamaConfig, Qwen3Config
+
+    torch.manual_seed(0)
+    kw = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4,
+              num_key_value_heads=n_kv, head_dim=16, vocab_size=160, max_position_embeddings=256,
+              tie_word_embeddings=False)
+    cfg = Qwen3Config(**kw) if qwen else LlamaConfig(**kw)
+    model = AutoModelForCausalLM.from_config(cfg).to(torch.bfloat16).eval()
+    # spread the channel scales so rank selection is not a coin flip on flat random-init scores
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for blk in model.model.layers:
+            blk.mlp.up_proj.weight.mul_(torch.exp(0.6 * torch.randn(128, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn.q_proj.weight.mul_(torch.exp(0.6 * torch.randn(64, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn.k_proj.weight.mul_(torch.exp(0.6 * torch.randn(16 * n_kv, 1, generator=g)).to(torch.bfloat16))
+            blk.input_layernorm.weight.mul_(torch.exp(0.5 * torch.randn(64, generator=g)).to(torch.bfloat16))
+    adapter = ref.ma.ModelAdapter.from_model(model, tokenizer=None)
+    tmp = tempfile.mkdtemp(prefix="mg_golden_")
+    adapter.config = ref.cc.CompressionConfig(
+        model="tiny", temp_storage_dir=tmp, order="mlp,qk,vo", calib_size=4, calibs_batch_size=2,
+        compression_ratio=0.3, max_sparsity=0.95, sparsity_smoothing=0.04948, ridge_vo=1e-5,
+        ridge_qk=1e-2, nystrom_ridge=1e-4)
+    gen = torch.Generator().manual_seed(1234)
+    tokens = torch.randint(0, 160, (4, 96), generator=gen)
+    adapter.calibs = [tokens[0:2], tokens[2:4]]
+
+    cap = {"mlp_in": [[] for _ in range(3)], "ln_out": [[] for _ in range(3)],
+           "q_out": [[] for _ in range(3)], "k_out": [[] for _ in range(3)]}
+    handles = []
+    for i, blk in enumerate(model.model.layers):
+        handles.append(blk.mlp.down_proj.register_forward_pre_hook(
+            lambda m, inp, i=i: cap["mlp_in"][i].append(inp[0].detach().clone())))
+        handles.append(blk.input_layernorm.register_forward_hook(
+            lambda m, inp, out, i=i: cap["ln_out"][i].append(out.detach().clone())))
+        handles.append(blk.self_attn.q_proj.register_forward_hook(
+            lambda m, inp, out, i=i: cap["q_out"][i].append(out.detach().clone())))
+        handles.append(blk.self_attn.k_proj.register_forward_hook(
+            lambda m, inp, out, i=i: cap["k_out"][i].append(out.detach().clone())))
+    hs_cap = []
+    orig_fwd = model.forward
+
+    def fwd(*a, **k):
+        o = orig_fwd(*a, **k)
+        hs_cap.append([h.detach().clone() for h in o.hidden_states])
+        return o
+
+    model.forward = fwd
+    cov_mlp, cov_q, cov_k, cov_x, bi = ref.cal.load_calibs(adapter, 4, 2, dataset="synthetic",
+                                                          target_layers=[0, 1, 2])
+    model.forward = orig_fwd
+    for h in handles:
+        h.remove()
+    keep = ref.cu.allocate_global_sparsity(bi, compression_ratio=0.3, smoothing=0.04948,
+                                           max_sparsity=0.95, adapter=adapter)
+    ref.mlp.compress_nystrom(adapter, cov_mlp, keep, [0, 1, 2])
+    masks = ref.qk.compress_qk(adapter, (cov_q, cov_k), keep, target_layers=[0, 1, 2])
+    ref.vo.compress_vo(adapter, cov_x, keep, target_layers=[0, 1, 2])
+
+    out = {"tokens": tokens.numpy(), "bi": np.array(bi), "keep": np.array(keep),
+           "cfg": np.array([64, 128, 3, 4, n_kv, 16, 160, int(qwen)])}
+    for k, v in model.state_dict().items():
+        out["w:" + k] = v.float().numpy()
+    for i in range(3):
+        out[f"cov_mlp{i}"], out[f"cov_q{i}"] = f64(cov_mlp[i]), f64(cov_q[i])
+        out[f"cov_k{i}"], out[f"cov_x{i}"] = f64(cov_k[i]), f64(cov_x[i])
+        for name in cap:
+            out[f"{name}{i}"] = torch.stack(cap[name][i]).float().numpy()     # [batches, B, T, n]
+        out[f"mask{i}"] = masks[i].numpy()
+        for suf in ("mlp", "qk", "vo"):
+            d = torch.load(os.path.join(tmp, f"layer_{i}_{suf}"))
+            for k, v in d.items():
+                out[f"L{i}_{suf}_{k}"] = v.float().numpy()
+    for b, hs in enumerate(hs_cap):
+        out[f"hidden{b}"] = torch.stack(hs).float().numpy()                    # [L+1, B, T, D]
+    np.savez_compressed(OUT / f"pipeline_{tag}.npz", **out)
+
+
+def main():
+    if not REF.exists():
+        raise SystemExit(f"{REF} not found: goldens can only be generated where the reference is mounted")
+    install_cpu_shim()
+    sys.path.insert(0, str(REF))
+    os.chdir(tempfile.mkdtemp(prefix="mg_golden_cwd_"))   # the reference writes ./metrics, ./logs
+    import src.adapters.CompressionConfig as cc
+    import src.adapters.model_adapter as ma
+    import src.calibration as cal
+    import src.compression.compress_mlp as mlp
+    import src.compression.compress_qk as qk
+    import src.compression.compress_vo as vo
+    import src.compression_utils as cu
+
+    ref = types.SimpleNamespace(cc=cc, ma=ma, cal=cal, mlp=mlp, qk=qk, vo=vo, cu=cu)
+    OUT.mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(20240917)
+    with torch.no_grad():
+        golden_utils(ref, rng)
+        golden_mlp(ref, rng)
+        golden_qk(ref, rng)
+        golden_vo(ref, rng)
+        golden_pipeline(ref, "llama_mha", n_kv=4)
+        golden_pipeline(ref, "llama_gqa", n_kv=2)
+        golden_pipeline(ref, "qwen3_gqa", n_kv=2, qwen=True)
+    for p in sorted(OUT.glob("*.npz")):
+        print(p.name, p.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,7 +86,9 @@ def allocate_global_sparsity(bi_scores, compression_ratio: float, smoothing: flo
     """softmax(-BI/eps) spreads a budget of L*ratio over the layers; layers above the cap are
     clamped and their excess handed to the uncapped ones in proportion to their softmax weight,
     repeated until nothing exceeds the cap.  Returns keep ratios (1 - sparsity)."""
-    s = np.asarray(bi_scores, dtype=np.float64)
+    # `torch.tensor(list_of_floats)` is float32: the scores are rounded to fp32 BEFORE the
+    # fp64 softmax (compression_utils.py:96) — a quirk that moves keep ratios by ~1e-8.
+    s = np.asarray(bi_scores, dtype=np.float64).astype(np.float32).astype(np.float64)
     z = -s / smoothing
     z = z - z.max()
     w = np.exp(z)
@@ -130,6 +132,9 @@ def ridge_scores(c: np.ndarray, ridge: float) -> np.ndarray:
     """diag((C + ridge*I)^-1) through a Cholesky factorisation (compress_mlp.py:13-25)."""
     c = np.asarray(c, dtype=np.float64)
     n = c.shape[0]
+    # `ridge * torch.eye(n)` is a float32 tensor in the reference (no dtype given), so the ridge
+    # that reaches the fp64 sum is float32(ridge).
+    ridge = float(np.float32(ridge))
     low = np.linalg.cholesky(c + ridge * np.eye(n))
     low_inv = np.linalg.solve(low, np.eye(n))  # any exact route to the inverse diagonal
     return np.sum(low_inv * low_inv, axis=0)
