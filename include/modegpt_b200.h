@@ -59,6 +59,64 @@ int mg_finalize_sym_f32(float* C, int64_t n, int64_t ldc, float scale, void* str
 /* scale a dense fp32 buffer in place (per-head blocks are already full). */
 int mg_scale_f32(float* x, int64_t count, float scale, void* stream);
 
+/* ---- type-I: Nystrom MLP ---------------------------------------------------------------------- */
+
+/* scores[j] = diag((C + ridge I)^-1)_j.  C: fp32 [n,n], upper triangle read.  Blocked Cholesky
+ * (fp64 128-wide diagonal blocks, tcgen05 TRSM + trailing SYRK on bf16x3 planes) and blocked
+ * triangular inverse.  *info (device int, caller zero-initialises) receives the 1-based index of
+ * the first non-positive pivot, else stays 0.
+ * Replaces get_ridge_scores, src/compression/compress_mlp.py:13-25. */
+size_t mg_ridge_scores_ws_bytes(int64_t n);
+int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, float* scores,
+                        void* ws, size_t ws_bytes, int* info, void* stream);
+
+/* idx_out[0..k) = indices of the k smallest (largest != 0: largest) scores in ASCENDING INDEX
+ * order; ties at the threshold resolve to the lower index.
+ * Replaces topk(largest=False) + sort, src/compression/compress_mlp.py:45-47. */
+int mg_select_k_f32(const float* scores, int64_t n, int64_t k, int largest, int64_t* idx_out,
+                    void* stream);
+
+/* out[i, :] = W[idx[i], :], bf16 rows of length d.
+ * Replaces W_u[topk, :], W_g[topk, :], src/compression/compress_mlp.py:49-50. */
+int mg_gather_rows_bf16(const void* W, int64_t ldw, const int64_t* idx, int64_t k, int64_t d,
+                        void* out, int64_t ldo, void* stream);
+
+/* Wd_out[d, k] (bf16) = ((C[idx,idx] + jitter I)^-1 (C[idx, :] Wd^T))^T.
+ * C: fp32 [n,n] FULL symmetric (both triangles valid); Wd: bf16 [d, n].
+ * Replaces src/compression/compress_mlp.py:52-57 (+ the transpose at :97). */
+size_t mg_nystrom_down_ws_bytes(int64_t n, int64_t k, int64_t d);
+int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* idx, int64_t k,
+                        const void* Wd, int64_t d, int64_t ldwd, float jitter, void* Wd_out,
+                        int64_t ld_out, void* ws, size_t ws_bytes, int* info, void* stream);
+
+/* ---- type-II: CR Q/K ------------------------------------------------------------------------- */
+
+/* mask[h, :] for every kv head.  mode 0 (llama / qwen, RoPE-paired): score_j = sum over the
+ * group's query heads of (Cq_jj + ridge_q)(Ck_jj + ridge_k) + same at j + hd/2; the top r/2 pairs
+ * in descending-score order give mask = cat(idx, idx + hd/2).  mode 1 (OPT): score_j =
+ * sqrt((Cq_jj + ridge_q)(Ck_jj + ridge_k)), top r.  Cq [H,hd,hd], Ck [KV,hd,hd] fp32; mask [KV,r].
+ * Replaces compress_head_llama_grouped / compress_head_llama / compress_head_opt,
+ * src/compression/compress_qk.py:320-476 (sqrt_M column norms == diagonal + ridge). */
+int mg_qk_select_f32(const float* Cq, const float* Ck, int n_heads, int n_kv_heads, int hd,
+                     int mode, float ridge_q, float ridge_k, int r, int64_t* mask, void* stream);
+
+/* out[q*r + t, :] = W[q*hd + mask[(q/group)*r + t], :] for q < n_heads, t < r.
+ * Replaces Q_heads[:, Sk_mask, :], K_head[Sk_mask, :], src/compression/compress_qk.py:369-376. */
+int mg_gather_head_rows_bf16(const void* W, int64_t ldw, const int64_t* mask, int n_heads,
+                             int group, int64_t hd, int64_t r, int64_t d, void* out, int64_t ldo,
+                             void* stream);
+
+/* ---- type-III: SVD V/O ----------------------------------------------------------------------- */
+
+/* Wv_out[KV*r, d], Wo_out[d, H*r] (bf16) from Cx [d,d] fp32 FULL symmetric, Wv [KV*hd, d],
+ * Wo [d, H*hd] (bf16).  GQA when n_heads != n_kv_heads, else the MHA two-stage form.
+ * Replaces compress_vo's per-layer body, src/compression/compress_vo.py:43-99,112-223. */
+size_t mg_vo_ws_bytes(int64_t d, int n_heads, int n_kv_heads, int hd);
+int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
+                   const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
+                   int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
+                   size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,7 @@ struct KParams {
   int pair_b[kMaxPairs];
   int atomic;
   int vec_ok;  // D and ldd allow float4 accesses
+  int klo_from_n;
 };
 
 struct Work {
@@ -78,8 +79,16 @@ __device__ __forceinline__ Work decode_work(const KParams& p, int w) {
     o.nj = nj;
     o.mi = tile - R * nj * (nj + 1) / 2;
   }
-  o.kb0 = ks * p.kb_per_split;
-  o.kb1 = min(p.kblocks, o.kb0 + p.kb_per_split);
+  if (p.klo_from_n) {
+    // the tile's own k range is [lo, kblocks); split it evenly (a split may come out empty)
+    const int lo = min(p.kblocks, (o.nj * BN) / BK);
+    const int per = (p.kblocks - lo + p.ksplit - 1) / p.ksplit;
+    o.kb0 = lo + ks * per;
+    o.kb1 = min(p.kblocks, o.kb0 + per);
+  } else {
+    o.kb0 = ks * p.kb_per_split;
+    o.kb1 = min(p.kblocks, o.kb0 + p.kb_per_split);
+  }
   return o;
 }
 
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const Work wk = decode_work<BN>(p, w);
+        if (wk.kb0 >= wk.kb1) continue;
         const int a_col = wk.mi * BM;
         const int b_col = wk.nj * BN;
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
@@ -160,10 +170,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const Work wk = decode_work<BN>(p, w);
+        if (wk.kb0 >= wk.kb1) continue;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
+        ++it;
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -196,10 +208,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     const int row_in_tile = q * 32 + lane;
     int it = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const Work wk = decode_work<BN>(p, w);
+      if (wk.kb0 >= wk.kb1) continue;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
+      ++it;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int64_t gr = static_cast<int64_t>(wk.mi) * BM + row_in_tile;
@@ -442,6 +456,7 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.kb_per_split = (kp.kblocks + ksplit - 1) / ksplit;
   kp.ksplit = (kp.kblocks + kp.kb_per_split - 1) / kp.kb_per_split;
   kp.atomic = kp.ksplit > 1;
+  kp.klo_from_n = a.klo_from_n;
   kp.total_work = kp.ntiles * kp.ksplit;
   kp.vec_ok = ((reinterpret_cast<uintptr_t>(a.D) & 15) == 0) &&
               (a.tiles == TILES_DIAG ? (kp.hd % 4 == 0) : (a.ldd % 4 == 0));

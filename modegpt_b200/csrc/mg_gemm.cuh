@@ -46,6 +46,9 @@ struct GemmArgs {
   int epi;     // EpiOp
   int hd;      // TILES_DIAG: block size (divides 128)
   int ksplit;  // >= 1; > 1 requires EPI_ADD (atomics); 0 = choose automatically
+  // B is lower-triangular in (k, n): B[k, n] == 0 for n > k, so an N tile starting at column c0
+  // only needs k >= c0 (used by the blocked triangular inverse).
+  int klo_from_n;
 };
 
 // Returns 0, a negative argument error, or -1000 - cudaError_t.

@@ -138,6 +138,8 @@ const char* mg_error_string(int code) {
     case -6: return "head dim must be 32, 64 or 128 and divide n";
     case -7: return "leading dimension smaller than row length";
     case -9: return "split-K requires accumulate mode";
+    case -10: return "workspace too small (see the *_ws_bytes query)";
+    case -11: return "invalid rank / head dimension / mode";
     case -90: return "cuTensorMapEncodeTiled unavailable (driver too old?)";
     case -92: return "bf16 operand must be 16-byte aligned with ld % 8 == 0";
     case -94: return "cuTensorMapEncodeTiled failed";

@@ -1,0 +1,613 @@
+// mg_type1.cu — type-I (Nystrom MLP) path, SURVEY §8 rows a7-a8:
+//   ridge-leverage scores diag((C + lambda I)^-1)      src/compression/compress_mlp.py:13-25
+//   k-smallest selection, ascending indices             src/compression/compress_mlp.py:45-47
+//   row gathers of W_up / W_gate                         src/compression/compress_mlp.py:49-50
+//   W_down' = (C_kk + 1e-6 I)^-1 C_k: W_down^T          src/compression/compress_mlp.py:52-57
+// Every O(n^3) step is a blocked algorithm whose block operations run on the tcgen05 engine with
+// fp32 operands split into three bf16 planes; the 128-wide diagonal blocks are done in fp64.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/modegpt_b200.h"
+#include "mg_gemm.cuh"
+#include "mg_linalg.cuh"
+
+namespace {
+
+using mg::kNB;
+using mg::kPlanes;
+using bf16 = __nv_bfloat16;
+
+inline int cuda_rc() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------- workspace carving
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+struct ScoresWs {
+  float* a;          // [n x np] working copy C + ridge I -> U
+  float* tt;         // [128 x np]
+  float* yrow;       // [128 x np]
+  bf16* y_planes;    // [3][np x np]
+  mg::CholWorkspace chol;
+  size_t bytes;
+};
+
+ScoresWs carve_scores(void* p, int64_t n) {
+  const int64_t np = mg::round_up(n, 64);
+  const int64_t panels = (n + kNB - 1) / kNB;
+  Carver c(p);
+  ScoresWs w{};
+  w.a = c.take<float>(n * np);
+  w.tt = c.take<float>(kNB * np);
+  w.yrow = c.take<float>(kNB * np);
+  w.y_planes = c.take<bf16>(kPlanes * np * np);
+  w.chol.u_planes = c.take<bf16>(kPlanes * np * np);
+  w.chol.l_planes = nullptr;
+  w.chol.w_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
+  w.chol.wt_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
+  w.chol.row_planes = c.take<bf16>(kPlanes * kNB * np);
+  w.chol.n_pad = np;
+  w.bytes = c.off + 256;
+  return w;
+}
+
+struct NystromWs {
+  bf16* g_planes;   // [3][n x kp]     planes of C[:, idx]
+  bf16* wdt;        // [n x dp]        W_down^T
+  float* rhs;       // [k x dp]        cross term -> Z -> X (in place)
+  float* ckk;       // [k x kp]
+  bf16* z_planes;   // [3][128 x dp]
+  mg::CholWorkspace chol;
+  size_t bytes;
+};
+
+NystromWs carve_nystrom(void* p, int64_t n, int64_t k, int64_t d) {
+  const int64_t kp = mg::round_up(k, 64), dp = mg::round_up(d, 64);
+  const int64_t panels = (k + kNB - 1) / kNB;
+  Carver c(p);
+  NystromWs w{};
+  w.g_planes = c.take<bf16>(kPlanes * n * kp);
+  w.wdt = c.take<bf16>(n * dp);
+  w.rhs = c.take<float>(k * dp);
+  w.ckk = c.take<float>(k * kp);
+  w.z_planes = c.take<bf16>(kPlanes * kNB * dp);
+  w.chol.u_planes = c.take<bf16>(kPlanes * kp * kp);
+  w.chol.l_planes = c.take<bf16>(kPlanes * kp * kp);
+  w.chol.w_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
+  w.chol.wt_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
+  w.chol.row_planes = c.take<bf16>(kPlanes * kNB * kp);
+  w.chol.n_pad = kp;
+  w.bytes = c.off + 256;
+  return w;
+}
+
+void pairs6(mg::GemmArgs& g) {
+  static const int pa[6] = {0, 0, 1, 1, 0, 2};
+  static const int pb[6] = {0, 1, 0, 1, 2, 0};
+  g.npairs = 6;
+  for (int i = 0; i < 6; ++i) {
+    g.pair_a[i] = pa[i];
+    g.pair_b[i] = pb[i];
+  }
+}
+
+// ------------------------------------------------------------------------------- small kernels
+__device__ __forceinline__ void split3(float x, bf16& hi, bf16& mid, bf16& lo) {
+  hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  mid = __float2bfloat16_rn(r1);
+  lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
+// dst (upper triangle) = src + ridge * I
+__global__ void copy_ridge_kernel(const float* __restrict__ src, int64_t lds,
+                                  float* __restrict__ dst, int64_t ldd, int64_t n, float ridge) {
+  const int64_t r = blockIdx.y;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < n;
+       c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (c >= r) dst[r * ldd + c] = src[r * lds + c] + (c == r ? ridge : 0.f);
+  }
+}
+
+// Y diagonal block := W_j^T (planes), and its contribution to the column sums of squares
+__global__ void __launch_bounds__(128) ydiag_kernel(const bf16* __restrict__ wt_planes,
+                                                    bf16* __restrict__ y_planes, int64_t np,
+                                                    int64_t j0, int nb,
+                                                    float* __restrict__ sumsq) {
+  const int c = threadIdx.x;
+  if (c >= nb) return;
+  float acc = 0.f;
+  for (int r = 0; r < nb; ++r) {
+    float v = 0.f;
+#pragma unroll
+    for (int p = 0; p < kPlanes; ++p) {
+      const bf16 x = wt_planes[p * kNB * kNB + r * kNB + c];
+      y_planes[p * np * np + (j0 + r) * np + (j0 + c)] = x;
+      v += __bfloat162float(x);
+    }
+    acc = fmaf(v, v, acc);
+  }
+  atomicAdd(sumsq + j0 + c, acc);
+}
+
+// out row (q*r + t) = W[q*hd + mask[(q/group)*r + t], :]   (plain row gather: hd = n rows, 1 head)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const bf16* __restrict__ W, int64_t ldw,
+                                                          const int64_t* __restrict__ mask,
+                                                          int group, int64_t hd, int64_t r,
+                                                          int64_t d, bf16* __restrict__ out,
+                                                          int64_t ldo, int vec) {
+  const int64_t orow = blockIdx.x;
+  const int64_t q = orow / r, t = orow - q * r;
+  const int64_t srow = q * hd + mask[(q / group) * r + t];
+  const bf16* s = W + srow * ldw;
+  bf16* o = out + orow * ldo;
+  if (vec) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+    for (int64_t i = threadIdx.x; i < (d >> 3); i += blockDim.x) o4[i] = __ldg(s4 + i);
+  } else {
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) o[i] = s[i];
+  }
+}
+
+// out[i, j] = C[idx_i, idx_j] + (i == j) * jitter, upper triangle only
+__global__ void __launch_bounds__(256) gather_sym_kernel(const float* __restrict__ C, int64_t ldc,
+                                                         const int64_t* __restrict__ idx,
+                                                         int64_t k, float* __restrict__ out,
+                                                         int64_t ldo, float jitter) {
+  const int64_t i = blockIdx.y;
+  const float* row = C + idx[i] * ldc;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < k;
+       j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (j >= i) out[i * ldo + j] = __ldg(row + idx[j]) + (i == j ? jitter : 0.f);
+  }
+}
+
+// planes_p[l, i] = p-th plane of C[l, idx_i]   for l in [0, n), i in [0, k)
+__global__ void __launch_bounds__(256) gather_cols_planes_kernel(const float* __restrict__ C,
+                                                                 int64_t ldc, int64_t n,
+                                                                 const int64_t* __restrict__ idx,
+                                                                 int64_t k,
+                                                                 bf16* __restrict__ planes,
+                                                                 int64_t ldp, int64_t pstride) {
+  const int64_t l = blockIdx.y;
+  const float* row = C + l * ldc;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < k;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    bf16 h, m, lo;
+    split3(__ldg(row + idx[i]), h, m, lo);
+    const int64_t o = l * ldp + i;
+    planes[o] = h;
+    planes[pstride + o] = m;
+    planes[2 * pstride + o] = lo;
+  }
+}
+
+// out[c, r] = in[r, c]; IN is bf16 or float, OUT is bf16
+template <class IN>
+__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const IN* __restrict__ in,
+                                                                int64_t ld_in, int64_t rows,
+                                                                int64_t cols,
+                                                                bf16* __restrict__ out,
+                                                                int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? static_cast<float>(in[r * ld_in + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t orow = c0 + i, ocol = r0 + tx;
+    if (orow < cols && ocol < rows) out[orow * ld_out + ocol] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------- radix select
+__device__ __forceinline__ uint32_t order_key(float x, int largest) {
+  uint32_t u = __float_as_uint(x);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order -> ascending uint
+  return largest ? ~u : u;
+}
+
+// idx_out[0..k) = indices of the k smallest (largest) scores, in ascending INDEX order; ties at the
+// threshold go to the lower indices.  Single CTA: n is a vector length (<= a few 1e5).
+__global__ void __launch_bounds__(1024, 1) select_k_kernel(const float* __restrict__ scores,
+                                                           int64_t n, int64_t k, int largest,
+                                                           int64_t* __restrict__ idx_out) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_mask;
+  __shared__ int64_t s_need;
+  __shared__ uint32_t warp_tot[32];
+  __shared__ int64_t base_less, base_eq;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    s_prefix = 0;
+    s_mask = 0;
+    s_need = k;
+    base_less = 0;
+    base_eq = 0;
+  }
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (t < 256) hist[t] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix, mask = s_mask;
+    for (int64_t i = t; i < n; i += 1024) {
+      const uint32_t u = order_key(scores[i], largest);
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      int64_t need = s_need, cum = 0;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (cum + hist[b] >= need) break;
+        cum += hist[b];
+      }
+      s_need = need - cum;
+      s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+      s_mask = mask | (255u << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = s_prefix;
+  const int64_t need_eq = s_need;
+  const int lane = t & 31, warp = t >> 5;
+  for (int64_t c0 = 0; c0 < n; c0 += 1024) {
+    const int64_t i = c0 + t;
+    uint32_t less = 0, eq = 0;
+    if (i < n) {
+      const uint32_t u = order_key(scores[i], largest);
+      less = u < thr;
+      eq = u == thr;
+    }
+    uint32_t v = less | (eq << 16);  // both counts fit in 16 bits per 1024-chunk
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_tot[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += y;
+      }
+      warp_tot[lane] = winc - w;  // exclusive
+    }
+    __syncthreads();
+    const uint32_t excl = inc - v + warp_tot[warp];
+    const int64_t less_before = base_less + (excl & 0xFFFFu);
+    const int64_t eq_before = base_eq + (excl >> 16);
+    const bool sel = less || (eq && eq_before < need_eq);
+    if (sel) idx_out[less_before + (eq_before < need_eq ? eq_before : need_eq)] = i;
+    __syncthreads();
+    if (t == 1023) {
+      const uint32_t tot = excl + v;
+      base_less += tot & 0xFFFFu;
+      base_eq += tot >> 16;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+size_t mg_ridge_scores_ws_bytes(int64_t n) { return carve_scores(nullptr, n).bytes; }
+
+int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, float* scores,
+                        void* ws, size_t ws_bytes, int* info, void* stream) {
+  if (!C || !scores || !ws || !info) return -1;
+  if (n <= 0) return -2;
+  if (ldc < n) return -7;
+  ScoresWs w = carve_scores(ws, n);
+  if (ws_bytes < w.bytes) return -10;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t np = w.chol.n_pad;
+  int rc;
+
+  copy_ridge_kernel<<<dim3(static_cast<unsigned>((n + 1023) / 1024 < 8 ? (n + 1023) / 1024 : 8),
+                           static_cast<unsigned>(n)),
+                      256, 0, s>>>(C, ldc, w.a, np, n, ridge);
+  if ((rc = cuda_rc())) return rc;
+  rc = mg::cholesky_upper(w.a, n, np, w.chol, info, s);
+  if (rc) return rc;
+
+  // ---- blocked inverse of U, stored transposed (Y = U^-T, lower) as bf16 planes; the scores are
+  //      the column sums of squares of Y.
+  cudaMemsetAsync(w.y_planes, 0, sizeof(bf16) * kPlanes * np * np, s);
+  cudaMemsetAsync(scores, 0, sizeof(float) * n, s);
+  const int64_t pstride = np * np;
+  const int64_t wstride = static_cast<int64_t>(kPlanes) * kNB * kNB;
+  for (int64_t j0 = 0, pj = 0; j0 < n; j0 += kNB, ++pj) {
+    const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
+    const bf16* wj = w.chol.w_planes + pj * wstride;
+    const bf16* wtj = w.chol.wt_planes + pj * wstride;
+    ydiag_kernel<<<1, 128, 0, s>>>(wtj, w.y_planes, np, j0, nb, scores);
+    if ((rc = cuda_rc())) return rc;
+    if (j0 == 0) continue;
+    // Tt[nb, j0] = U[0:j0, jb]^T * Y[0:j0, 0:j0]
+    cudaMemsetAsync(w.tt, 0, sizeof(float) * kNB * np, s);
+    mg::GemmArgs g{};
+    g.A = w.chol.u_planes + j0;
+    g.lda = np;
+    g.a_plane_stride = pstride;
+    g.a_planes = kPlanes;
+    g.B = w.y_planes;
+    g.ldb = np;
+    g.b_plane_stride = pstride;
+    g.b_planes = kPlanes;
+    pairs6(g);
+    g.M = nb;
+    g.N = j0;
+    g.K = j0;
+    g.D = w.tt;
+    g.ldd = np;
+    g.alpha = 1.f;
+    g.tiles = mg::TILES_FULL;
+    g.epi = mg::EPI_ADD;
+    g.ksplit = 0;
+    g.klo_from_n = 1;
+    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    if ((rc = mg::split_planes(w.tt, np, nb, j0, w.chol.row_planes, np, kNB * np, false, nullptr, s)))
+      return rc;
+    // Y[jb, 0:j0] = -W_j^T * Tt
+    mg::GemmArgs h{};
+    h.A = wj;
+    h.lda = kNB;
+    h.a_plane_stride = kNB * kNB;
+    h.a_planes = kPlanes;
+    h.B = w.chol.row_planes;
+    h.ldb = np;
+    h.b_plane_stride = kNB * np;
+    h.b_planes = kPlanes;
+    pairs6(h);
+    h.M = nb;
+    h.N = j0;
+    h.K = nb;
+    h.D = w.yrow;
+    h.ldd = np;
+    h.alpha = -1.f;
+    h.tiles = mg::TILES_FULL;
+    h.epi = mg::EPI_STORE;
+    h.ksplit = 1;
+    if ((rc = mg::gemm_tn_launch(h, s))) return rc;
+    if ((rc = mg::split_planes(w.yrow, np, nb, j0, w.y_planes + j0 * np, np, pstride, false, scores,
+                               s)))
+      return rc;
+  }
+  return 0;
+}
+
+int mg_select_k_f32(const float* scores, int64_t n, int64_t k, int largest, int64_t* idx_out,
+                    void* stream) {
+  if (!scores || !idx_out) return -1;
+  if (n <= 0 || k < 0 || k > n) return -2;
+  if (k == 0) return 0;
+  select_k_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(scores, n, k, largest,
+                                                                      idx_out);
+  return cuda_rc();
+}
+
+int mg_gather_rows_bf16(const void* W, int64_t ldw, const int64_t* idx, int64_t k, int64_t d,
+                        void* out, int64_t ldo, void* stream) {
+  if (!W || !idx || !out) return -1;
+  if (k <= 0 || d <= 0) return -2;
+  if (ldw < d || ldo < d) return -7;
+  const int vec = (d % 8 == 0) && (ldw % 8 == 0) && (ldo % 8 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(W) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  // hd is irrelevant with a single "head": q = 0 for every output row
+  gather_rows_kernel<<<static_cast<unsigned>(k), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(W), ldw, idx, 1, 0, k, d, static_cast<bf16*>(out), ldo, vec);
+  return cuda_rc();
+}
+
+int mg_gather_head_rows_bf16(const void* W, int64_t ldw, const int64_t* mask, int n_heads,
+                             int group, int64_t hd, int64_t r, int64_t d, void* out, int64_t ldo,
+                             void* stream) {
+  if (!W || !mask || !out) return -1;
+  if (n_heads <= 0 || group <= 0 || hd <= 0 || r <= 0 || d <= 0) return -2;
+  if (ldw < d || ldo < d) return -7;
+  const int vec = (d % 8 == 0) && (ldw % 8 == 0) && (ldo % 8 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(W) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  gather_rows_kernel<<<static_cast<unsigned>(n_heads * r), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(W), ldw, mask, group, hd, r, d, static_cast<bf16*>(out), ldo, vec);
+  return cuda_rc();
+}
+
+size_t mg_nystrom_down_ws_bytes(int64_t n, int64_t k, int64_t d) {
+  return carve_nystrom(nullptr, n, k, d).bytes;
+}
+
+int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* idx, int64_t k,
+                        const void* Wd, int64_t d, int64_t ldwd, float jitter, void* Wd_out,
+                        int64_t ld_out, void* ws, size_t ws_bytes, int* info, void* stream) {
+  if (!C || !idx || !Wd || !Wd_out || !ws || !info) return -1;
+  if (n <= 0 || k <= 0 || k > n || d <= 0) return -2;
+  if (ldc < n || ldwd < n || ld_out < k) return -7;
+  NystromWs w = carve_nystrom(ws, n, k, d);
+  if (ws_bytes < w.bytes) return -10;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t kp = w.chol.n_pad, dp = mg::round_up(d, 64);
+  int rc;
+
+  // operands of the cross term  rhs[k, d] = C[idx, :] W_down^T = (C[:, idx])^T (W_down^T)
+  gather_cols_planes_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
+                                   static_cast<unsigned>(n)),
+                              256, 0, s>>>(C, ldc, n, idx, k, w.g_planes, kp, n * kp);
+  if ((rc = cuda_rc())) return rc;
+  transpose_to_bf16_kernel<bf16><<<dim3(static_cast<unsigned>((n + 31) / 32),
+                                        static_cast<unsigned>((d + 31) / 32)),
+                                   256, 0, s>>>(static_cast<const bf16*>(Wd), ldwd, d, n, w.wdt, dp);
+  if ((rc = cuda_rc())) return rc;
+  {
+    mg::GemmArgs g{};
+    g.A = w.g_planes;
+    g.lda = kp;
+    g.a_plane_stride = n * kp;
+    g.a_planes = kPlanes;
+    g.B = w.wdt;
+    g.ldb = dp;
+    g.b_planes = 1;
+    g.npairs = 3;
+    for (int i = 0; i < 3; ++i) {
+      g.pair_a[i] = i;
+      g.pair_b[i] = 0;
+    }
+    g.M = k;
+    g.N = d;
+    g.K = n;
+    g.D = w.rhs;
+    g.ldd = dp;
+    g.alpha = 1.f;
+    g.tiles = mg::TILES_FULL;
+    g.epi = mg::EPI_STORE;
+    g.ksplit = 1;
+    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+  }
+  // C_kk + jitter I and its Cholesky factor (planes of U and of L = U^T)
+  gather_sym_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
+                           static_cast<unsigned>(k)),
+                      256, 0, s>>>(C, ldc, idx, k, w.ckk, kp, jitter);
+  if ((rc = cuda_rc())) return rc;
+  if ((rc = mg::cholesky_upper(w.ckk, k, kp, w.chol, info, s))) return rc;
+
+  const int64_t pstride = kp * kp;
+  const int64_t wstride = static_cast<int64_t>(kPlanes) * kNB * kNB;
+  const int64_t panels = (k + kNB - 1) / kNB;
+  // ---- forward solve  U^T Z = rhs  (right-looking, in place)
+  for (int64_t pi = 0; pi < panels; ++pi) {
+    const int64_t i0 = pi * kNB;
+    const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+    float* bi = w.rhs + i0 * dp;
+    if ((rc = mg::split_planes(bi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
+    mg::GemmArgs g{};
+    g.A = w.chol.w_planes + pi * wstride;  // Z_i = W_i^T B_i
+    g.lda = kNB;
+    g.a_plane_stride = kNB * kNB;
+    g.a_planes = kPlanes;
+    g.B = w.z_planes;
+    g.ldb = dp;
+    g.b_plane_stride = kNB * dp;
+    g.b_planes = kPlanes;
+    pairs6(g);
+    g.M = nb;
+    g.N = d;
+    g.K = nb;
+    g.D = bi;
+    g.ldd = dp;
+    g.alpha = 1.f;
+    g.tiles = mg::TILES_FULL;
+    g.epi = mg::EPI_STORE;
+    g.ksplit = 1;
+    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    const int64_t rest = k - i0 - nb;
+    if (rest <= 0) break;
+    if ((rc = mg::split_planes(bi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
+    mg::GemmArgs t{};
+    t.A = w.chol.u_planes + i0 * kp + (i0 + nb);  // B[rest] -= U[ib, rest]^T Z_i
+    t.lda = kp;
+    t.a_plane_stride = pstride;
+    t.a_planes = kPlanes;
+    t.B = w.z_planes;
+    t.ldb = dp;
+    t.b_plane_stride = kNB * dp;
+    t.b_planes = kPlanes;
+    pairs6(t);
+    t.M = rest;
+    t.N = d;
+    t.K = nb;
+    t.D = w.rhs + (i0 + nb) * dp;
+    t.ldd = dp;
+    t.alpha = -1.f;
+    t.tiles = mg::TILES_FULL;
+    t.epi = mg::EPI_ADD;
+    t.ksplit = 1;
+    if ((rc = mg::gemm_tn_launch(t, s))) return rc;
+  }
+  // ---- backward solve  U X = Z
+  for (int64_t pi = panels - 1; pi >= 0; --pi) {
+    const int64_t i0 = pi * kNB;
+    const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+    float* zi = w.rhs + i0 * dp;
+    if ((rc = mg::split_planes(zi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
+    mg::GemmArgs g{};
+    g.A = w.chol.wt_planes + pi * wstride;  // X_i = W_i Z_i  (A[k, m] = W_i[m, k])
+    g.lda = kNB;
+    g.a_plane_stride = kNB * kNB;
+    g.a_planes = kPlanes;
+    g.B = w.z_planes;
+    g.ldb = dp;
+    g.b_plane_stride = kNB * dp;
+    g.b_planes = kPlanes;
+    pairs6(g);
+    g.M = nb;
+    g.N = d;
+    g.K = nb;
+    g.D = zi;
+    g.ldd = dp;
+    g.alpha = 1.f;
+    g.tiles = mg::TILES_FULL;
+    g.epi = mg::EPI_STORE;
+    g.ksplit = 1;
+    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    if (i0 == 0) break;
+    if ((rc = mg::split_planes(zi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
+    mg::GemmArgs t{};
+    t.A = w.chol.l_planes + i0 * kp;  // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
+    t.lda = kp;
+    t.a_plane_stride = pstride;
+    t.a_planes = kPlanes;
+    t.B = w.z_planes;
+    t.ldb = dp;
+    t.b_plane_stride = kNB * dp;
+    t.b_planes = kPlanes;
+    pairs6(t);
+    t.M = i0;
+    t.N = d;
+    t.K = nb;
+    t.D = w.rhs;
+    t.ldd = dp;
+    t.alpha = -1.f;
+    t.tiles = mg::TILES_FULL;
+    t.epi = mg::EPI_ADD;
+    t.ksplit = 1;
+    if ((rc = mg::gemm_tn_launch(t, s))) return rc;
+  }
+  // ---- W_down' [d, k] = X^T, bf16
+  transpose_to_bf16_kernel<float><<<dim3(static_cast<unsigned>((d + 31) / 32),
+                                         static_cast<unsigned>((k + 31) / 32)),
+                                    256, 0, s>>>(w.rhs, dp, k, d, static_cast<bf16*>(Wd_out), ld_out);
+  return cuda_rc();
+}
+
+}  // extern "C"

@@ -84,3 +84,137 @@ def scale_(x: torch.Tensor, scale: float) -> None:
     if x.dtype != torch.float32 or not x.is_contiguous():
         raise ValueError("scale_: x must be contiguous float32")
     check("mg_scale_f32", lib.mg_scale_f32(x.data_ptr(), x.numel(), scale, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# decompositions
+# ------------------------------------------------------------------------------------------------
+class NotPositiveDefinite(RuntimeError):
+    """A Cholesky pivot was <= 0 (the reference's torch.linalg.cholesky raises here too)."""
+
+    def __init__(self, what: str, pivot: int):
+        super().__init__(f"{what}: matrix not positive definite at pivot {pivot}")
+        self.pivot = pivot
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def _f32_square(C: torch.Tensor, name: str) -> tuple[int, int]:
+    n, m, ld = _rowmajor_2d(C, name)
+    if n != m or C.dtype != torch.float32:
+        raise ValueError(f"{name} must be a square float32 matrix")
+    return n, ld
+
+
+def ridge_scores(C: torch.Tensor, ridge: float, what: str = "ridge_scores") -> torch.Tensor:
+    """diag((C + ridge I)^-1) as float32 [n]; C float32 [n, n] (upper triangle is read)."""
+    n, ldc = _f32_square(C, "C")
+    scores = torch.empty(n, dtype=torch.float32, device=C.device)
+    info = torch.zeros(1, dtype=torch.int32, device=C.device)
+    nbytes = lib.mg_ridge_scores_ws_bytes(n)
+    ws = _workspace(nbytes, C.device)
+    check("mg_ridge_scores_f32",
+          lib.mg_ridge_scores_f32(C.data_ptr(), n, ldc, ridge, scores.data_ptr(), ws.data_ptr(),
+                                  nbytes, info.data_ptr(), _stream()))
+    piv = int(info.item())
+    if piv:
+        raise NotPositiveDefinite(what, piv)
+    return scores
+
+
+def select_k(scores: torch.Tensor, k: int, largest: bool = False) -> torch.Tensor:
+    """indices (int64, ascending) of the k smallest / largest entries of a float32 vector."""
+    if scores.dtype != torch.float32 or scores.dim() != 1 or not scores.is_contiguous():
+        raise ValueError("select_k: scores must be a contiguous float32 vector")
+    idx = torch.empty(k, dtype=torch.int64, device=scores.device)
+    check("mg_select_k_f32",
+          lib.mg_select_k_f32(scores.data_ptr(), scores.numel(), k, int(largest), idx.data_ptr(),
+                              _stream()))
+    return idx
+
+
+def gather_rows(W: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """W[idx, :] for a bf16 matrix and int64 device indices."""
+    rows, d, ldw = _rowmajor_2d(W, "W")
+    if W.dtype != torch.bfloat16 or idx.dtype != torch.int64:
+        raise TypeError("gather_rows: W must be bfloat16 and idx int64")
+    out = torch.empty(idx.numel(), d, dtype=torch.bfloat16, device=W.device)
+    check("mg_gather_rows_bf16",
+          lib.mg_gather_rows_bf16(W.data_ptr(), ldw, idx.data_ptr(), idx.numel(), d,
+                                  out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+def nystrom_down(C: torch.Tensor, idx: torch.Tensor, Wd: torch.Tensor,
+                 jitter: float = 1e-6) -> torch.Tensor:
+    """((C[idx,idx] + jitter I)^-1 C[idx,:] Wd^T)^T as bf16 [d, k]; C full symmetric float32."""
+    n, ldc = _f32_square(C, "C")
+    d, n2, ldwd = _rowmajor_2d(Wd, "Wd")
+    if n2 != n or Wd.dtype != torch.bfloat16:
+        raise ValueError("nystrom_down: Wd must be bfloat16 [d, n]")
+    k = idx.numel()
+    out = torch.empty(d, k, dtype=torch.bfloat16, device=C.device)
+    info = torch.zeros(1, dtype=torch.int32, device=C.device)
+    nbytes = lib.mg_nystrom_down_ws_bytes(n, k, d)
+    ws = _workspace(nbytes, C.device)
+    check("mg_nystrom_down_f32",
+          lib.mg_nystrom_down_f32(C.data_ptr(), n, ldc, idx.data_ptr(), k, Wd.data_ptr(), d, ldwd,
+                                  jitter, out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes,
+                                  info.data_ptr(), _stream()))
+    piv = int(info.item())
+    if piv:
+        raise NotPositiveDefinite("nystrom_down", piv)
+    return out
+
+
+def qk_select(Cq: torch.Tensor, Ck: torch.Tensor, r: int, mode: int, ridge_q: float,
+              ridge_k: float) -> torch.Tensor:
+    """Rotary mask [KV, r] (int64).  mode 0 = RoPE-paired (llama/qwen), 1 = OPT."""
+    if Cq.dtype != torch.float32 or Ck.dtype != torch.float32:
+        raise TypeError("qk_select: statistics must be float32")
+    if not (Cq.is_contiguous() and Ck.is_contiguous()) or Cq.dim() != 3 or Ck.dim() != 3:
+        raise ValueError("qk_select: Cq/Ck must be contiguous [heads, hd, hd]")
+    H, hd = Cq.shape[0], Cq.shape[1]
+    KV = Ck.shape[0]
+    mask = torch.empty(KV, r, dtype=torch.int64, device=Cq.device)
+    check("mg_qk_select_f32",
+          lib.mg_qk_select_f32(Cq.data_ptr(), Ck.data_ptr(), H, KV, hd, mode, ridge_q, ridge_k, r,
+                               mask.data_ptr(), _stream()))
+    return mask
+
+
+def gather_head_rows(W: torch.Tensor, mask: torch.Tensor, n_heads: int, group: int,
+                     hd: int) -> torch.Tensor:
+    """out[q*r + t] = W[q*hd + mask[q // group, t]] for every head q."""
+    rows, d, ldw = _rowmajor_2d(W, "W")
+    if W.dtype != torch.bfloat16 or mask.dtype != torch.int64 or not mask.is_contiguous():
+        raise TypeError("gather_head_rows: W bfloat16, mask contiguous int64")
+    r = mask.shape[1]
+    out = torch.empty(n_heads * r, d, dtype=torch.bfloat16, device=W.device)
+    check("mg_gather_head_rows_bf16",
+          lib.mg_gather_head_rows_bf16(W.data_ptr(), ldw, mask.data_ptr(), n_heads, group, hd, r,
+                                       d, out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+def vo_compress(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int,
+                n_kv_heads: int, hd: int, r: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Type-III factors: (v_proj [KV*r, d], o_proj [d, H*r]) in bf16.  Cx full symmetric."""
+    d, ldc = _f32_square(Cx, "Cx")
+    _, _, ldwv = _rowmajor_2d(Wv, "Wv")
+    _, _, ldwo = _rowmajor_2d(Wo, "Wo")
+    if Wv.dtype != torch.bfloat16 or Wo.dtype != torch.bfloat16:
+        raise TypeError("vo_compress: weights must be bfloat16")
+    if Wv.shape != (n_kv_heads * hd, d) or Wo.shape != (d, n_heads * hd):
+        raise ValueError("vo_compress: weight shapes do not match the head layout")
+    v_out = torch.empty(n_kv_heads * r, d, dtype=torch.bfloat16, device=Cx.device)
+    o_out = torch.empty(d, n_heads * r, dtype=torch.bfloat16, device=Cx.device)
+    nbytes = lib.mg_vo_ws_bytes(d, n_heads, n_kv_heads, hd)
+    ws = _workspace(nbytes, Cx.device)
+    check("mg_vo_compress",
+          lib.mg_vo_compress(Cx.data_ptr(), ldc, ridge, Wv.data_ptr(), ldwv, Wo.data_ptr(), ldwo,
+                             n_heads, n_kv_heads, hd, d, r, v_out.data_ptr(), v_out.stride(0),
+                             o_out.data_ptr(), o_out.stride(0), ws.data_ptr(), nbytes, _stream()))
+    return v_out, o_out
