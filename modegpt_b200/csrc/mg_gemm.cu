@@ -34,7 +34,8 @@ struct Cfg {
   static constexpr uint32_t b_bytes = (BN / 64) * kBoxBytes;
   static constexpr uint32_t stage_bytes = kABytes + b_bytes;
   static constexpr int stages = (BN == 256) ? 4 : 6;
-  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 + 512;
+  static constexpr uint32_t epi_bytes = 4 * 2 * 4096;  // per epilogue warp: 2 x (32 x 32 fp32)
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + epi_bytes + 1024 + 512;
 };
 
 struct KParams {
@@ -51,6 +52,7 @@ struct KParams {
   int atomic;
   int vec_ok;  // D and ldd allow float4 accesses
   int klo_from_n;
+  int tma_epi;  // epilogue through swizzled smem + TMA store / reduce-add
 };
 
 struct Work {
@@ -95,12 +97,13 @@ __device__ __forceinline__ Work decode_work(const KParams& p, int w) {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const KParams p) {
+                   const __grid_constant__ CUtensorMap tmD, const KParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
+  uint8_t* epi_smem = smem + C::stages * C::stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + C::epi_bytes);
   uint64_t* empty = full + C::stages;
   uint64_t* tmem_full = empty + C::stages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_epi) tma_prefetch_desc(&tmD);
     for (int s = 0; s < C::stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -219,6 +223,45 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t gr = static_cast<int64_t>(wk.mi) * BM + row_in_tile;
       const int64_t warp_row0 = static_cast<int64_t>(wk.mi) * BM + q * 32;
       const bool row_ok = gr < p.M;
+      if (p.tma_epi) {
+        // TMEM -> registers -> 128B-swizzled staging tile -> TMA store / L2 reduce-add.
+        // TMA clips at the tensor bounds; in TILES_UPPER chunks that straddle the diagonal are
+        // written whole (the strict lower triangle is unspecified by contract).
+        uint8_t* wbuf = epi_smem + (warp - 2) * 8192;
+        if (warp_row0 < p.M) {
+#pragma unroll 1
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
+            if (gc0 >= p.N) break;
+            if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
+            float v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>(as * BN + cc * 32);
+            tmem_ld_32x32(taddr, v);
+            tmem_ld_wait();
+            uint8_t* buf = wbuf + (cc & 1) * 4096;
+            if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has read `buf`
+            __syncwarp();
+            uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2],
+                              p.alpha * v[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int c0 = (p.tiles == TILES_DIAG) ? cc * 32 : static_cast<int>(gc0);
+              if (p.epi == EPI_STORE) tma_store_2d(&tmD, buf, c0, static_cast<int>(warp_row0));
+              else tma_reduce_add_2d(&tmD, buf, c0, static_cast<int>(warp_row0));
+              bulk_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+        continue;
+      }
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
@@ -311,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
+  if (warp >= 2 && lane == 0 && p.tma_epi) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -362,9 +406,23 @@ int make_plane_map(CUtensorMap* tm, const __nv_bfloat16* base, int64_t cols, int
   return r == CUDA_SUCCESS ? 0 : -94;
 }
 
+// 2D fp32 map of the output for the TMA epilogue: 32 x 32 boxes, 128B swizzle.
+int make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64_t ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -90;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -94;
+}
+
 template <int BN>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp,
-                cudaStream_t stream) {
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                const KParams& kp, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -374,7 +432,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& k
     attr_set = true;
   }
   const int grid = kp.total_work < device_sm_count() ? kp.total_work : device_sm_count();
-  gemm_tn_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, kp);
+  gemm_tn_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, tmD, kp);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
 }
@@ -466,7 +524,17 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_plane_map(&tmB, a.B, a.N, a.K, a.ldb, a.b_planes, a.b_plane_stride);
   if (rc) return rc;
-  return bn256 ? launch_impl<256>(tmA, tmB, kp, stream) : launch_impl<128>(tmA, tmB, kp, stream);
+  // TMA epilogue whenever the output is a plain 2D fp32 tile grid with 16-byte aligned rows
+  CUtensorMap tmD = tmA;
+  const bool diag128 = a.tiles == TILES_DIAG && kp.hd == 128;
+  if (((reinterpret_cast<uintptr_t>(a.D) & 15) == 0) &&
+      (diag128 || (a.tiles != TILES_DIAG && a.ldd % 4 == 0))) {
+    rc = diag128 ? make_out_map(&tmD, a.D, 128, a.M, 128) : make_out_map(&tmD, a.D, a.N, a.M, a.ldd);
+    if (rc) return rc;
+    kp.tma_epi = 1;
+  }
+  return bn256 ? launch_impl<256>(tmA, tmB, tmD, kp, stream)
+               : launch_impl<128>(tmA, tmB, tmD, kp, stream);
 }
 
 }  // namespace mg
