@@ -84,113 +84,224 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// diagonal block: fp64 Cholesky (upper) + in-place triangular inverse, one CTA of 1024 threads
+// potrf128: Cholesky of one 128 x 128 diagonal block, fp64, one CTA of 512 threads.
+// Four 32-wide sub-panels; per sub-panel
+//   (1) warp 0 factors the 32 x 32 diagonal block entirely in registers (lane k owns column k,
+//       pivot row broadcast by shuffles),
+//   (2) one thread per remaining column does the 32-step forward substitution,
+//   (3) all threads apply the rank-32 update to the trailing part of the block.
 // ---------------------------------------------------------------------------------------------
 constexpr int kDiagLd = kNB + 1;
-constexpr size_t kDiagSmem = sizeof(double) * (kNB * kDiagLd + 2 * kNB);
+constexpr int kPotrfThreads = 512;
+constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 32);
 
-__global__ void __launch_bounds__(1024, 1)
-    diag_block_kernel(float* __restrict__ A, int64_t ld, int64_t j0, int nb,
-                      __nv_bfloat16* __restrict__ w_planes, __nv_bfloat16* __restrict__ wt_planes,
-                      __nv_bfloat16* __restrict__ u_planes, __nv_bfloat16* __restrict__ l_planes,
-                      int64_t ld_up, int64_t up_plane_stride, int* __restrict__ info) {
+__global__ void __launch_bounds__(kPotrfThreads, 1)
+    potrf128_kernel(float* __restrict__ A, int64_t ld, int64_t j0, int nb,
+                    float* __restrict__ t_fwd, float* __restrict__ t_bwd,
+                    __nv_bfloat16* __restrict__ u_planes, __nv_bfloat16* __restrict__ l_planes,
+                    int64_t ld_up, int64_t up_plane_stride, int* __restrict__ info) {
   extern __shared__ double sm[];
-  double* a = sm;                       // [128][129]
-  double* u = sm + kNB * kDiagLd;       // [128] scaled pivot row / copied column
+  double* a = sm;                     // [128][129], upper triangle live
+  double* invd = sm + kNB * kDiagLd;  // [32] reciprocal pivots of the current sub-panel
   const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
 
-  // load the upper triangle; pad a short last block with the identity
-  for (int e = t; e < kNB * kNB; e += 1024) {
+  for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
     const int i = e >> 7, k = e & 127;
-    double v = (i == k) ? 1.0 : 0.0;
+    double v = (i == k) ? 1.0 : 0.0;  // identity padding for a short last block
     if (i < nb && k < nb && i <= k) v = static_cast<double>(A[(j0 + i) * ld + (j0 + k)]);
     a[i * kDiagLd + k] = v;
   }
-
-  // ---- Cholesky, right-looking: a = U^T U, U upper
-  const int ti = t >> 5, tk = t & 31;
-  for (int j = 0; j < nb; ++j) {
-    __syncthreads();
-    double piv = a[j * kDiagLd + j];
-    if (!(piv > 0.0)) {
-      if (t == 0) atomicCAS(info, 0, static_cast<int>(j0 + j + 1));
-      piv = 1e-30;
-    }
-    const double d = sqrt(piv);
-    const double inv = 1.0 / d;
-    if (t < kNB) u[t] = (t > j && t < nb) ? a[j * kDiagLd + t] * inv : 0.0;
-    __syncthreads();
-    if (t < kNB) {
-      if (t > j && t < nb) a[j * kDiagLd + t] = u[t];
-      if (t == j) a[j * kDiagLd + j] = d;
-    }
-    for (int i = j + 1 + ti; i < nb; i += 32) {
-      const double ui = u[i];
-      for (int k = i + tk; k < nb; k += 32) a[i * kDiagLd + k] -= ui * u[k];
-    }
-  }
   __syncthreads();
 
-  // ---- write U11 (fp32, upper triangle only) and its planes
-  for (int e = t; e < kNB * kNB; e += 1024) {
+  const int nsub = (nb + 31) / 32;
+  for (int kb = 0; kb < nsub; ++kb) {
+    const int c0 = kb * 32;
+    if (warp == 0) {
+      double col[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) col[i] = (i <= lane) ? a[(c0 + i) * kDiagLd + c0 + lane] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        double piv = __shfl_sync(0xffffffffu, col[j], j);
+        if (!(piv > 0.0)) {
+          if (lane == 0 && c0 + j < nb) atomicCAS(info, 0, static_cast<int>(j0 + c0 + j + 1));
+          piv = 1e-30;
+        }
+        const double d = sqrt(piv);
+        const double inv = 1.0 / d;
+        const double ujk = (lane > j) ? col[j] * inv : (lane == j ? d : 0.0);
+        col[j] = ujk;
+        if (lane == j) invd[j] = inv;
+#pragma unroll
+        for (int i = j + 1; i < 32; ++i) {
+          const double uji = __shfl_sync(0xffffffffu, ujk, i);
+          col[i] -= uji * ujk;  // entries with i > lane are never read
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i <= lane) a[(c0 + i) * kDiagLd + c0 + lane] = col[i];
+    }
+    __syncthreads();
+    const int rest = kNB - c0 - 32;  // columns right of the sub-panel (padding included)
+    if (t < rest) {
+      const int k = c0 + 32 + t;
+      double x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        double s = a[(c0 + i) * kDiagLd + k];
+#pragma unroll
+        for (int m = 0; m < i; ++m) s -= a[(c0 + m) * kDiagLd + c0 + i] * x[m];
+        x[i] = s * invd[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[(c0 + i) * kDiagLd + k] = x[i];
+    }
+    __syncthreads();
+    // rank-32 update of the trailing upper triangle
+    for (int e = t; e < rest * rest; e += kPotrfThreads) {
+      const int ii = e / rest, kk = e - ii * rest;
+      if (ii > kk) continue;
+      const int i = c0 + 32 + ii, k = c0 + 32 + kk;
+      double s = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < 32; ++m) s += a[(c0 + m) * kDiagLd + i] * a[(c0 + m) * kDiagLd + k];
+      a[i * kDiagLd + k] -= s;
+    }
+    __syncthreads();
+  }
+
+  // ---- outputs
+  for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
     const int i = e >> 7, k = e & 127;
-    if (i < nb && k < nb) {
-      const float x = (i <= k) ? static_cast<float>(a[i * kDiagLd + k]) : 0.f;
-      if (i <= k) A[(j0 + i) * ld + (j0 + k)] = x;
-      if (u_planes || l_planes) {
+    const bool in = i < nb && k < nb;
+    const float x = (in && i <= k) ? static_cast<float>(a[i * kDiagLd + k]) : 0.f;
+    if (in && i <= k) A[(j0 + i) * ld + (j0 + k)] = x;
+    // forward block: T[m][i] = U[m][i]; identity beyond nb
+    t_fwd[i * kTLd + k] = in ? x : (i == k ? 1.f : 0.f);
+    if (in && (u_planes || l_planes)) {
+      __nv_bfloat16 h, m, l;
+      split3(x, h, m, l);
+      if (u_planes) {
+        const int64_t o = (j0 + i) * ld_up + (j0 + k);
+        u_planes[o] = h;
+        u_planes[up_plane_stride + o] = m;
+        u_planes[2 * up_plane_stride + o] = l;
+      }
+      if (l_planes) {
+        const int64_t o = (j0 + k) * ld_up + (j0 + i);
+        l_planes[o] = h;
+        l_planes[up_plane_stride + o] = m;
+        l_planes[2 * up_plane_stride + o] = l;
+      }
+    }
+  }
+  // backward block: T'[m'][i'] = U[nb-1-i'][nb-1-m'] for m' <= i' < nb; identity beyond
+  for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
+    const int mp = e >> 7, ip = e & 127;
+    float x = (mp == ip) ? 1.f : 0.f;
+    if (mp < nb && ip < nb)
+      x = (mp <= ip) ? static_cast<float>(a[(nb - 1 - ip) * kDiagLd + (nb - 1 - mp)]) : 0.f;
+    t_bwd[mp * kTLd + ip] = x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trsm128: forward substitution with a compact lower-in-(m,i) block T (x_i = (b_i - sum_{m<i}
+// T[m][i] x_m) / T[i][i]), one thread per right-hand-side column, 32-row chunks held in
+// registers, earlier chunks' solutions parked in shared memory.  `reversed` maps chunk row i' to
+// matrix row nb-1-i' (that is how U x = b becomes a forward substitution).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTrsmThreads = 128;
+constexpr size_t kTrsmSmem = sizeof(float) * (kTBlock + kNB * kTrsmThreads + kNB);
+
+__global__ void __launch_bounds__(kTrsmThreads)
+    trsm128_kernel(const float* __restrict__ tblock, int reversed, int nb,
+                   const float* __restrict__ B, int64_t ldb, int64_t ncols, float alpha,
+                   float* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ planes,
+                   int64_t ldp, int64_t pstride, __nv_bfloat16* __restrict__ tplanes,
+                   int64_t ldtp, int64_t tpstride, float* __restrict__ colsumsq) {
+  extern __shared__ __align__(16) float smf[];
+  float* T = smf;                        // [128][132]
+  float* xs = smf + kTBlock;             // [128][kTrsmThreads]
+  float* invd = xs + kNB * kTrsmThreads; // [128]
+  const int tid = threadIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(tblock);
+    float4* dst = reinterpret_cast<float4*>(T);
+    for (int e = tid; e < kTBlock / 4; e += kTrsmThreads) dst[e] = __ldg(src + e);
+  }
+  __syncthreads();
+  if (tid < kNB) invd[tid] = 1.f / T[tid * kTLd + tid];
+  __syncthreads();
+
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * kTrsmThreads + tid;
+  const bool valid = c < ncols;
+  const int nchunks = (nb + 31) / 32;
+  float sumsq = 0.f;
+  for (int rb = 0; rb < nchunks; ++rb) {
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int ip = rb * 32 + i;
+      const int row = reversed ? nb - 1 - ip : ip;
+      r[i] = (valid && ip < nb) ? B[static_cast<int64_t>(row) * ldb + c] : 0.f;
+    }
+    for (int pb = 0; pb < rb; ++pb) {
+#pragma unroll 4
+      for (int m = 0; m < 32; ++m) {
+        const float xm = xs[(pb * 32 + m) * kTrsmThreads + tid];
+        const float4* t4 = reinterpret_cast<const float4*>(T + (pb * 32 + m) * kTLd + rb * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 tv = t4[q];
+          r[4 * q + 0] = fmaf(-tv.x, xm, r[4 * q + 0]);
+          r[4 * q + 1] = fmaf(-tv.y, xm, r[4 * q + 1]);
+          r[4 * q + 2] = fmaf(-tv.z, xm, r[4 * q + 2]);
+          r[4 * q + 3] = fmaf(-tv.w, xm, r[4 * q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int ip = rb * 32 + i;
+      const float x = r[i] * invd[ip];
+      r[i] = x;
+      xs[ip * kTrsmThreads + tid] = x;
+      const float* trow = T + ip * kTLd + rb * 32;
+#pragma unroll
+      for (int i2 = i + 1; i2 < 32; ++i2) r[i2] = fmaf(-trow[i2], x, r[i2]);
+    }
+    if (!valid) continue;
+    // ---- outputs of this chunk
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int ip = rb * 32 + i;
+      if (ip >= nb) break;
+      const int row = reversed ? nb - 1 - ip : ip;
+      const float x = alpha * r[i];
+      sumsq = fmaf(x, x, sumsq);
+      if (X) X[static_cast<int64_t>(row) * ldx + c] = x;
+      if (planes || tplanes) {
         __nv_bfloat16 h, m, l;
         split3(x, h, m, l);
-        if (u_planes) {
-          const int64_t o = (j0 + i) * ld_up + (j0 + k);
-          u_planes[o] = h;
-          u_planes[up_plane_stride + o] = m;
-          u_planes[2 * up_plane_stride + o] = l;
+        if (planes) {
+          const int64_t o = static_cast<int64_t>(row) * ldp + c;
+          planes[o] = h;
+          planes[pstride + o] = m;
+          planes[2 * pstride + o] = l;
         }
-        if (l_planes) {
-          const int64_t o = (j0 + k) * ld_up + (j0 + i);
-          l_planes[o] = h;
-          l_planes[up_plane_stride + o] = m;
-          l_planes[2 * up_plane_stride + o] = l;
+        if (tplanes) {
+          const int64_t o = c * ldtp + row;
+          tplanes[o] = h;
+          tplanes[tpstride + o] = m;
+          tplanes[2 * tpstride + o] = l;
         }
       }
     }
   }
-  __syncthreads();
-
-  // ---- in-place inverse of the upper-triangular factor, column by column:
-  //      W[0:j, j] = -W[0:j, 0:j] * U[0:j, j] / U[j, j];  8 threads share each row's dot product
-  const int row = t >> 3, part = t & 7;
-  for (int j = 0; j < nb; ++j) {
-    if (t < j) u[t] = a[t * kDiagLd + j];
-    __syncthreads();
-    const double wjj = 1.0 / a[j * kDiagLd + j];
-    double s = 0.0;
-    if (row < j)
-      for (int k = row + part; k < j; k += 8) s += a[row * kDiagLd + k] * u[k];
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    __syncthreads();
-    if (part == 0 && row < j) a[row * kDiagLd + j] = -s * wjj;
-    if (t == 0) a[j * kDiagLd + j] = wjj;
-  }
-  __syncthreads();
-
-  // ---- emit W and W^T planes ([128 x 128], zero outside the upper triangle / beyond nb)
-  for (int e = t; e < kNB * kNB; e += 1024) {
-    const int i = e >> 7, k = e & 127;
-    float x = 0.f;
-    if (i < nb && k < nb && i <= k) x = static_cast<float>(a[i * kDiagLd + k]);
-    __nv_bfloat16 h, m, l;
-    split3(x, h, m, l);
-    w_planes[e] = h;
-    w_planes[kNB * kNB + e] = m;
-    w_planes[2 * kNB * kNB + e] = l;
-    const int et = k * kNB + i;
-    wt_planes[et] = h;
-    wt_planes[kNB * kNB + et] = m;
-    wt_planes[2 * kNB * kNB + et] = l;
-  }
+  if (colsumsq && valid) atomicAdd(colsumsq + c, sumsq);
 }
 
 }  // namespace
@@ -209,19 +320,37 @@ int split_planes(const float* src, int64_t ld_src, int64_t rows, int64_t cols, _
   return cuda_rc();
 }
 
-int diag_block_factor(float* A, int64_t ld, int64_t j0, int nb, __nv_bfloat16* w_planes,
-                      __nv_bfloat16* wt_planes, __nv_bfloat16* u_planes, __nv_bfloat16* l_planes,
-                      int64_t ld_up, int64_t up_plane_stride, int* info, cudaStream_t s) {
+int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd,
+             __nv_bfloat16* u_planes, __nv_bfloat16* l_planes, int64_t ld_up,
+             int64_t up_plane_stride, int* info, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(diag_block_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kDiagSmem));
+    cudaError_t e = cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kPotrfSmem));
     if (e != cudaSuccess) return -1000 - static_cast<int>(e);
     attr_set = true;
   }
-  diag_block_kernel<<<1, 1024, kDiagSmem, s>>>(A, ld, j0, nb, w_planes, wt_planes, u_planes,
-                                               l_planes, ld_up, up_plane_stride, info);
+  potrf128_kernel<<<1, kPotrfThreads, kPotrfSmem, s>>>(A, ld, j0, nb, t_fwd, t_bwd, u_planes,
+                                                       l_planes, ld_up, up_plane_stride, info);
+  return cuda_rc();
+}
+
+int trsm128(const float* tblock, bool reversed, int nb, const float* B, int64_t ldb, int64_t ncols,
+            float alpha, float* X, int64_t ldx, __nv_bfloat16* planes, int64_t ldp, int64_t pstride,
+            __nv_bfloat16* tplanes, int64_t ldtp, int64_t tpstride, float* colsumsq,
+            cudaStream_t s) {
+  if (ncols <= 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kTrsmSmem));
+    if (e != cudaSuccess) return -1000 - static_cast<int>(e);
+    attr_set = true;
+  }
+  const unsigned grid = static_cast<unsigned>((ncols + kTrsmThreads - 1) / kTrsmThreads);
+  trsm128_kernel<<<grid, kTrsmThreads, kTrsmSmem, s>>>(tblock, reversed ? 1 : 0, nb, B, ldb, ncols,
+                                                       alpha, X, ldx, planes, ldp, pstride, tplanes,
+                                                       ldtp, tpstride, colsumsq);
   return cuda_rc();
 }
 
@@ -241,50 +370,22 @@ int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int
                    cudaStream_t s) {
   const int64_t np = ws.n_pad;
   const int64_t pstride = np * np;
-  const int64_t wstride = static_cast<int64_t>(kPlanes) * kNB * kNB;
   int rc;
   for (int64_t j0 = 0, pj = 0; j0 < n; j0 += kNB, ++pj) {
     const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
-    __nv_bfloat16* wj = ws.w_planes + pj * wstride;
-    __nv_bfloat16* wtj = ws.wt_planes + pj * wstride;
-    rc = diag_block_factor(A, ld, j0, nb, wj, wtj, ws.u_planes, ws.l_planes, np, pstride, info, s);
+    float* tf = ws.t_fwd + pj * kTBlock;
+    float* tb = ws.t_bwd + pj * kTBlock;
+    rc = potrf128(A, ld, j0, nb, tf, tb, ws.u_planes, ws.l_planes, np, pstride, info, s);
     if (rc) return rc;
     const int64_t rest = n - j0 - nb;
     if (rest <= 0) break;
+    // block row: U12 = U11^-T A12 (in place) + its bf16 planes (and those of U12^T)
     float* a12 = A + j0 * ld + (j0 + nb);
-    // TRSM as a GEMM with the inverted diagonal block: U12 = W^T A12
-    rc = split_planes(a12, ld, nb, rest, ws.row_planes, np, kNB * np, false, nullptr, s);
-    if (rc) return rc;
-    GemmArgs g{};
-    g.A = wj;
-    g.lda = kNB;
-    g.a_plane_stride = kNB * kNB;
-    g.a_planes = kPlanes;
-    g.B = ws.row_planes;
-    g.ldb = np;
-    g.b_plane_stride = kNB * np;
-    g.b_planes = kPlanes;
-    set_pairs6(g);
-    g.M = nb;
-    g.N = rest;
-    g.K = nb;
-    g.D = a12;
-    g.ldd = ld;
-    g.alpha = 1.f;
-    g.tiles = TILES_FULL;
-    g.epi = EPI_STORE;
-    g.ksplit = 1;
-    rc = gemm_tn_launch(g, s);
-    if (rc) return rc;
-    // planes of the finished block row (and of its transpose when the caller wants L = U^T)
     __nv_bfloat16* u12 = ws.u_planes + j0 * np + (j0 + nb);
-    rc = split_planes(a12, ld, nb, rest, u12, np, pstride, false, nullptr, s);
+    __nv_bfloat16* l21 = ws.l_planes ? ws.l_planes + (j0 + nb) * np + j0 : nullptr;
+    rc = trsm128(tf, false, nb, a12, ld, rest, 1.f, a12, ld, u12, np, pstride, l21, np, pstride,
+                 nullptr, s);
     if (rc) return rc;
-    if (ws.l_planes) {
-      rc = split_planes(a12, ld, nb, rest, ws.l_planes + (j0 + nb) * np + j0, np, pstride, true,
-                        nullptr, s);
-      if (rc) return rc;
-    }
     // trailing update on the upper triangle: A22 -= U12^T U12
     GemmArgs t{};
     t.A = t.B = u12;

@@ -1,6 +1,6 @@
 // mg_linalg.cuh — internal interface of the dense linear-algebra building blocks (mg_linalg.cu):
-// bf16 plane splitting, the 128-wide diagonal-block factor/invert kernel, the blocked Cholesky
-// driver, gathers, transposes and the radix select.
+// bf16 plane splitting, the 128-wide diagonal-block Cholesky kernel, the fused triangular-solve
+// panel kernel and the blocked Cholesky driver.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -10,6 +10,8 @@ namespace mg {
 
 constexpr int kNB = 128;      // panel width of every blocked algorithm
 constexpr int kPlanes = 3;    // fp32 = hi + mid + lo bf16 planes (24 mantissa bits)
+constexpr int kTLd = 132;     // leading dimension of the compact triangular blocks (float4 rows)
+constexpr int kTBlock = kNB * kTLd;
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -19,27 +21,41 @@ int split_planes(const float* src, int64_t ld_src, int64_t rows, int64_t cols, _
                  int64_t ld_dst, int64_t plane_stride, bool transpose, float* colsumsq,
                  cudaStream_t s, float diag_add = 0.f);
 
-// Factor the nb x nb (nb <= 128) diagonal block at (j0, j0) of the fp32 matrix A (upper, in
-// place, fp64 arithmetic in shared memory), and emit W = U11^-1 as bf16 planes: w_planes holds
-// W row-major [128 x 128] (x3), wt_planes holds W^T.  On a non-positive pivot the 1-based global
-// index is recorded in *info (first failure wins) and the pivot is clamped so nothing is NaN.
-// u_planes (optional) receives the bf16 planes of U11 (zeros below the diagonal) at the same
-// coordinates as in A, leading dimension ld_up; l_planes (optional) the transpose.
-int diag_block_factor(float* A, int64_t ld, int64_t j0, int nb, __nv_bfloat16* w_planes,
-                      __nv_bfloat16* wt_planes, __nv_bfloat16* u_planes, __nv_bfloat16* l_planes,
-                      int64_t ld_up, int64_t up_plane_stride, int* info, cudaStream_t s);
+// Cholesky of the nb x nb (nb <= 128) diagonal block at (j0, j0) of the fp32 matrix A: upper
+// factor U11 written back in place (upper triangle), fp64 arithmetic, hierarchical 32-blocking
+// (register-resident 32x32 factorisation by one warp, substitution + rank-32 update by the CTA).
+// Also emits
+//   t_fwd [128 x 132] fp32 : T[m][i] = U11[m][i]                (solves U11^T x = b)
+//   t_bwd [128 x 132] fp32 : T[m'][i'] = U11[nb-1-i'][nb-1-m']  (solves U11 x = b, reversed rows)
+// both identity-padded beyond nb, and (optionally) bf16 planes of U11 / U11^T at the block's
+// coordinates inside u_planes / l_planes (leading dimension ld_up).
+// A non-positive pivot records its 1-based global index in *info (first failure wins).
+int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd,
+             __nv_bfloat16* u_planes, __nv_bfloat16* l_planes, int64_t ld_up,
+             int64_t up_plane_stride, int* info, cudaStream_t s);
+
+// Triangular solve with one compact 128-block against many right-hand-side columns, one thread
+// per column:  X = alpha * T^-1 B  where T is t_fwd (rows in natural order) or t_bwd (reversed).
+//   B    [nb x ncols] fp32 (ldb)            right-hand sides
+//   X    [nb x ncols] fp32 (ldx), optional  (may alias B)
+//   planes  [3][nb x ncols] bf16 (ldp, pstride), optional: planes of X at [row][col]
+//   tplanes [3][ncols x nb] bf16 (ldtp, tpstride), optional: planes of X^T at [col][row]
+//   colsumsq[ncols], optional: += sum_rows X^2
+int trsm128(const float* tblock, bool reversed, int nb, const float* B, int64_t ldb, int64_t ncols,
+            float alpha, float* X, int64_t ldx, __nv_bfloat16* planes, int64_t ldp, int64_t pstride,
+            __nv_bfloat16* tplanes, int64_t ldtp, int64_t tpstride, float* colsumsq,
+            cudaStream_t s);
 
 struct CholWorkspace {
   // all device pointers, carved from the caller's workspace
   __nv_bfloat16* u_planes;   // [3][n_pad x n_pad]  planes of U (upper), ld = n_pad
   __nv_bfloat16* l_planes;   // [3][n_pad x n_pad]  planes of U^T (optional, may be null)
-  __nv_bfloat16* w_planes;   // [npanels][3][128 x 128]  W_j = U_jj^-1
-  __nv_bfloat16* wt_planes;  // [npanels][3][128 x 128]  W_j^T
-  __nv_bfloat16* row_planes; // [3][128 x n_pad] scratch
+  float* t_fwd;              // [npanels][128 x 132]
+  float* t_bwd;              // [npanels][128 x 132]
   int64_t n_pad;
 };
 
-// A (fp32, n x n, upper triangle) -> U with U^T U = A, in place; fills ws planes.
+// A (fp32, n x n, upper triangle) -> U with U^T U = A, in place; fills ws.
 int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int* info,
                    cudaStream_t s);
 

@@ -41,7 +41,7 @@ struct Carver {
 struct ScoresWs {
   float* a;          // [n x np] working copy C + ridge I -> U
   float* tt;         // [128 x np]
-  float* yrow;       // [128 x np]
+  float* ident;      // [128 x 128] identity (right-hand side for the diagonal blocks of U^-T)
   bf16* y_planes;    // [3][np x np]
   mg::CholWorkspace chol;
   size_t bytes;
@@ -54,13 +54,12 @@ ScoresWs carve_scores(void* p, int64_t n) {
   ScoresWs w{};
   w.a = c.take<float>(n * np);
   w.tt = c.take<float>(kNB * np);
-  w.yrow = c.take<float>(kNB * np);
+  w.ident = c.take<float>(kNB * kNB);
   w.y_planes = c.take<bf16>(kPlanes * np * np);
   w.chol.u_planes = c.take<bf16>(kPlanes * np * np);
   w.chol.l_planes = nullptr;
-  w.chol.w_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
-  w.chol.wt_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
-  w.chol.row_planes = c.take<bf16>(kPlanes * kNB * np);
+  w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
+  w.chol.t_bwd = c.take<float>(panels * mg::kTBlock);
   w.chol.n_pad = np;
   w.bytes = c.off + 256;
   return w;
@@ -88,9 +87,8 @@ NystromWs carve_nystrom(void* p, int64_t n, int64_t k, int64_t d) {
   w.z_planes = c.take<bf16>(kPlanes * kNB * dp);
   w.chol.u_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.l_planes = c.take<bf16>(kPlanes * kp * kp);
-  w.chol.w_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
-  w.chol.wt_planes = c.take<bf16>(panels * kPlanes * kNB * kNB);
-  w.chol.row_planes = c.take<bf16>(kPlanes * kNB * kp);
+  w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
+  w.chol.t_bwd = c.take<float>(panels * mg::kTBlock);
   w.chol.n_pad = kp;
   w.bytes = c.off + 256;
   return w;
@@ -124,25 +122,9 @@ __global__ void copy_ridge_kernel(const float* __restrict__ src, int64_t lds,
   }
 }
 
-// Y diagonal block := W_j^T (planes), and its contribution to the column sums of squares
-__global__ void __launch_bounds__(128) ydiag_kernel(const bf16* __restrict__ wt_planes,
-                                                    bf16* __restrict__ y_planes, int64_t np,
-                                                    int64_t j0, int nb,
-                                                    float* __restrict__ sumsq) {
-  const int c = threadIdx.x;
-  if (c >= nb) return;
-  float acc = 0.f;
-  for (int r = 0; r < nb; ++r) {
-    float v = 0.f;
-#pragma unroll
-    for (int p = 0; p < kPlanes; ++p) {
-      const bf16 x = wt_planes[p * kNB * kNB + r * kNB + c];
-      y_planes[p * np * np + (j0 + r) * np + (j0 + c)] = x;
-      v += __bfloat162float(x);
-    }
-    acc = fmaf(v, v, acc);
-  }
-  atomicAdd(sumsq + j0 + c, acc);
+__global__ void identity_kernel(float* __restrict__ m, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n * n) m[e] = (e / n == e % n) ? 1.f : 0.f;
 }
 
 // out row (q*r + t) = W[q*hd + mask[(q/group)*r + t], :]   (plain row gather: hd = n rows, 1 head)
@@ -344,13 +326,15 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
   cudaMemsetAsync(w.y_planes, 0, sizeof(bf16) * kPlanes * np * np, s);
   cudaMemsetAsync(scores, 0, sizeof(float) * n, s);
   const int64_t pstride = np * np;
-  const int64_t wstride = static_cast<int64_t>(kPlanes) * kNB * kNB;
+  identity_kernel<<<(kNB * kNB + 255) / 256, 256, 0, s>>>(w.ident, kNB);
+  if ((rc = cuda_rc())) return rc;
   for (int64_t j0 = 0, pj = 0; j0 < n; j0 += kNB, ++pj) {
     const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
-    const bf16* wj = w.chol.w_planes + pj * wstride;
-    const bf16* wtj = w.chol.wt_planes + pj * wstride;
-    ydiag_kernel<<<1, 128, 0, s>>>(wtj, w.y_planes, np, j0, nb, scores);
-    if ((rc = cuda_rc())) return rc;
+    const float* tf = w.chol.t_fwd + pj * mg::kTBlock;
+    // diagonal block Y[jb, jb] = U_jj^-T (solve U_jj^T X = I)
+    if ((rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
+                          w.y_planes + j0 * np + j0, np, pstride, nullptr, 0, 0, scores + j0, s)))
+      return rc;
     if (j0 == 0) continue;
     // Tt[nb, j0] = U[0:j0, jb]^T * Y[0:j0, 0:j0]
     cudaMemsetAsync(w.tt, 0, sizeof(float) * kNB * np, s);
@@ -375,31 +359,9 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
     g.ksplit = 0;
     g.klo_from_n = 1;
     if ((rc = mg::gemm_tn_launch(g, s))) return rc;
-    if ((rc = mg::split_planes(w.tt, np, nb, j0, w.chol.row_planes, np, kNB * np, false, nullptr, s)))
-      return rc;
-    // Y[jb, 0:j0] = -W_j^T * Tt
-    mg::GemmArgs h{};
-    h.A = wj;
-    h.lda = kNB;
-    h.a_plane_stride = kNB * kNB;
-    h.a_planes = kPlanes;
-    h.B = w.chol.row_planes;
-    h.ldb = np;
-    h.b_plane_stride = kNB * np;
-    h.b_planes = kPlanes;
-    pairs6(h);
-    h.M = nb;
-    h.N = j0;
-    h.K = nb;
-    h.D = w.yrow;
-    h.ldd = np;
-    h.alpha = -1.f;
-    h.tiles = mg::TILES_FULL;
-    h.epi = mg::EPI_STORE;
-    h.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(h, s))) return rc;
-    if ((rc = mg::split_planes(w.yrow, np, nb, j0, w.y_planes + j0 * np, np, pstride, false, scores,
-                               s)))
+    // Y[jb, 0:j0] = -U_jj^-T Tt : planes + column sums of squares in one pass
+    if ((rc = mg::trsm128(tf, false, nb, w.tt, np, j0, -1.f, nullptr, 0, w.y_planes + j0 * np, np,
+                          pstride, nullptr, 0, 0, scores, s)))
       return rc;
   }
   return 0;
@@ -502,37 +464,18 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   if ((rc = mg::cholesky_upper(w.ckk, k, kp, w.chol, info, s))) return rc;
 
   const int64_t pstride = kp * kp;
-  const int64_t wstride = static_cast<int64_t>(kPlanes) * kNB * kNB;
   const int64_t panels = (k + kNB - 1) / kNB;
   // ---- forward solve  U^T Z = rhs  (right-looking, in place)
   for (int64_t pi = 0; pi < panels; ++pi) {
     const int64_t i0 = pi * kNB;
     const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
     float* bi = w.rhs + i0 * dp;
-    if ((rc = mg::split_planes(bi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
-    mg::GemmArgs g{};
-    g.A = w.chol.w_planes + pi * wstride;  // Z_i = W_i^T B_i
-    g.lda = kNB;
-    g.a_plane_stride = kNB * kNB;
-    g.a_planes = kPlanes;
-    g.B = w.z_planes;
-    g.ldb = dp;
-    g.b_plane_stride = kNB * dp;
-    g.b_planes = kPlanes;
-    pairs6(g);
-    g.M = nb;
-    g.N = d;
-    g.K = nb;
-    g.D = bi;
-    g.ldd = dp;
-    g.alpha = 1.f;
-    g.tiles = mg::TILES_FULL;
-    g.epi = mg::EPI_STORE;
-    g.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
     const int64_t rest = k - i0 - nb;
+    // Z_i = U_ii^-T B_i (+ planes of Z_i for the update below)
+    if ((rc = mg::trsm128(w.chol.t_fwd + pi * mg::kTBlock, false, nb, bi, dp, d, 1.f, bi, dp,
+                          rest > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr, s)))
+      return rc;
     if (rest <= 0) break;
-    if ((rc = mg::split_planes(bi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
     mg::GemmArgs t{};
     t.A = w.chol.u_planes + i0 * kp + (i0 + nb);  // B[rest] -= U[ib, rest]^T Z_i
     t.lda = kp;
@@ -559,29 +502,10 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
     const int64_t i0 = pi * kNB;
     const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
     float* zi = w.rhs + i0 * dp;
-    if ((rc = mg::split_planes(zi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
-    mg::GemmArgs g{};
-    g.A = w.chol.wt_planes + pi * wstride;  // X_i = W_i Z_i  (A[k, m] = W_i[m, k])
-    g.lda = kNB;
-    g.a_plane_stride = kNB * kNB;
-    g.a_planes = kPlanes;
-    g.B = w.z_planes;
-    g.ldb = dp;
-    g.b_plane_stride = kNB * dp;
-    g.b_planes = kPlanes;
-    pairs6(g);
-    g.M = nb;
-    g.N = d;
-    g.K = nb;
-    g.D = zi;
-    g.ldd = dp;
-    g.alpha = 1.f;
-    g.tiles = mg::TILES_FULL;
-    g.epi = mg::EPI_STORE;
-    g.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    if ((rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
+                          i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr, s)))
+      return rc;
     if (i0 == 0) break;
-    if ((rc = mg::split_planes(zi, dp, nb, d, w.z_planes, dp, kNB * dp, false, nullptr, s))) return rc;
     mg::GemmArgs t{};
     t.A = w.chol.l_planes + i0 * kp;  // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
     t.lda = kp;
