@@ -1,0 +1,88 @@
+"""Run configuration: the reference's `CompressionConfig` surface, re-authored.
+
+Every field name and default of the reference dataclass is kept (src/adapters/CompressionConfig.py:8-35)
+so its recipes (`tests.sh:87-133`) run unchanged: each public field becomes `--<field>`, booleans are
+`store_true`.  Additive fields (marked NEW) drive what the reference cannot do: synthetic data with no
+network, token-sharded calibration and layer-distributed decomposition over `torch.distributed`.
+"""
+from __future__ import annotations
+
+import argparse
+import dataclasses
+import typing
+from dataclasses import dataclass, field
+from typing import Optional
+
+
+@dataclass
+class CompressionConfig:
+    model: str = "facebook/opt-6.7b"
+    device: int = 0
+    factorize_src_model: str = ""
+    nystrom_src_model: str = ""
+    tokenizer_src: str = "mistralai/Mixtral-8x7B-v0.1"
+    output_dir: str = "compressed_output"
+    temp_storage_dir: str = "./compressed_output/layers/"
+    dataset: str = "wikitext"
+    nystrom_ridge: float = 1e-2
+    order: Optional[str] = None
+    calib_size: int = 32
+    calibs_batch_size: int = 4
+    compression_ratio: float = 0.5
+    note: str = "NA"
+    max_sparsity: float = 0.8
+    sparsity_smoothing: float = 0.15
+    ridge_vo: float = 1e-4
+    ridge_qk: float = 1e-6
+    debug: bool = False
+    # ---- NEW (additive) -------------------------------------------------------------------------
+    seq_len: int = 2048            # synthetic sequence length (the 2048 normaliser is NOT changed)
+    eval_samples: int = 16         # held-out synthetic sequences for the perplexity check
+    seed: int = 1234               # calibration token seed (reference seeds are 1234)
+    keep_layers_in_memory: bool = False   # hand layers to convert_model without the disk round trip
+
+    _HELP: typing.ClassVar[dict] = {
+        "order": "mlp,qk,vo  -- <method>,<method>,<method>",
+        "dataset": "wikitext | c4 | alpha | synthetic (seeded random token ids; no network)",
+    }
+
+    # -- argparse bridge ---------------------------------------------------------------------------
+    @staticmethod
+    def _scalar_type(tp):
+        args = [a for a in typing.get_args(tp) if a is not type(None)]
+        return args[0] if args else tp
+
+    @classmethod
+    def make_parser(cls, parser: argparse.ArgumentParser | None = None) -> argparse.ArgumentParser:
+        parser = parser or argparse.ArgumentParser(description="MoDeGPT compression (B200-native)")
+        hints = typing.get_type_hints(cls)
+        for f in dataclasses.fields(cls):
+            if f.name.startswith("_"):
+                continue
+            tp = cls._scalar_type(hints[f.name])
+            if tp is bool:
+                parser.add_argument(f"--{f.name}", action="store_true", default=f.default)
+            else:
+                parser.add_argument(f"--{f.name}", type=tp, default=f.default,
+                                    help=cls._HELP.get(f.name))
+        return parser
+
+    @classmethod
+    def from_args(cls, args=None) -> "CompressionConfig":
+        ns = cls.make_parser().parse_args(args)
+        names = {f.name for f in dataclasses.fields(cls) if f.init}
+        return cls(**{k: v for k, v in vars(ns).items() if k in names})
+
+    # -- dict-style access used throughout the reference -------------------------------------------
+    def get(self, key: str, default=None):
+        val = getattr(self, key, default)
+        return default if val is None else val
+
+    def __getitem__(self, key: str):
+        return getattr(self, key)
+
+    def __contains__(self, key: str) -> bool:
+        return hasattr(self, key)
+
+    def to_dict(self) -> dict:
+        return {f.name: getattr(self, f.name) for f in dataclasses.fields(self)}

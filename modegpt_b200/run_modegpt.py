@@ -1,0 +1,140 @@
+"""CLI / orchestrator: `python -m modegpt_b200.run_modegpt ...` (alias `python -m src.run_modegpt`).
+
+Same flow and flags as the reference's `main` (src/run_modegpt.py:72-196): load -> baseline ppl ->
+[calibrate -> allocate -> type I / II / III] per window of <= 48 layers -> convert_model ->
+patch_config -> save -> reload through the Rebuild class -> compressed ppl -> metrics.
+Under `torchrun` the calibration tokens are sharded over ranks and each layer is decomposed by its
+owner; rank 0 converts, saves and evaluates.
+"""
+from __future__ import annotations
+
+import gc
+import logging
+import os
+import time
+
+import torch
+
+from . import distributed as D
+from .adapters.CompressionConfig import CompressionConfig
+from .adapters.model_adapter import ModelAdapter
+from .calibration import load_calibs
+from .compression.compress_mlp import compress_nystrom
+from .compression.compress_qk import compress_qk
+from .compression.compress_vo import compress_vo
+from .compression_utils import allocate_global_sparsity
+from .eval import compute_perplexity
+from .model_utils import reload_compressed_model, save_compressed_model
+
+logger = logging.getLogger("MoDeGPT")
+LAYERS_PER_STEP = 48  # src/run_modegpt.py:107
+
+
+def _setup_logging():
+    logger.setLevel(logging.INFO)
+    if not logger.handlers:
+        h = logging.StreamHandler()
+        h.setFormatter(logging.Formatter("%(asctime)s - %(levelname)s - %(message)s"))
+        logger.addHandler(h)
+
+
+def _init_distributed(cfg: CompressionConfig) -> str:
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        if not torch.distributed.is_initialized():
+            torch.distributed.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        return f"cuda:{local}"
+    torch.cuda.set_device(cfg.device)
+    return f"cuda:{cfg.device}"
+
+
+@torch.no_grad()
+def main(trial=None, config: CompressionConfig | None = None):
+    _setup_logging()
+    gc.collect()
+    config = config or CompressionConfig.from_args()
+    device = _init_distributed(config)
+    is_root = D.rank() == 0
+    if is_root:
+        print(config.to_dict())
+    if not config.order:
+        raise SystemExit('--order is required, e.g. --order "mlp,qk,vo"')
+
+    model, tokenizer = reload_compressed_model(config.model, device=device)
+    adapter = ModelAdapter.from_model(model=model, tokenizer=tokenizer)
+    adapter.config = config
+    adapter.metrics["note"] = config.note
+
+    if is_root:
+        baseline = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
+        logger.info(f"Baseline ppl: {baseline}")
+        adapter.metrics["baseline-ppl"] = baseline
+
+    n_layers = adapter.n_layers
+    save_dir = os.path.join(config.output_dir, "model")
+    rotary_masks: list = []
+    timings = {"calibration_s": 0.0, "mlp_s": 0.0, "qk_s": 0.0, "vo_s": 0.0}
+
+    def timed(key, fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        timings[key] += time.perf_counter() - t0
+        return out
+
+    for start in range(0, n_layers, LAYERS_PER_STEP):
+        target = list(range(start, min(n_layers, start + LAYERS_PER_STEP)))
+        cov_mlp, cov_q, cov_k, cov_x, bi_scores = timed("calibration_s", lambda: load_calibs(
+            adapter=adapter, n_samples=config.calib_size, batch_size=config.calibs_batch_size,
+            dataset=config.dataset, target_layers=target))
+        keep = allocate_global_sparsity(bi_scores, compression_ratio=config.compression_ratio,
+                                        smoothing=config.sparsity_smoothing,
+                                        max_sparsity=config.max_sparsity, adapter=adapter)
+        if "mlp" in config.order:
+            timed("mlp_s", lambda: compress_nystrom(adapter=adapter, cov=cov_mlp, keep_ratios=keep,
+                                                    target_layers=target))
+        if "qk" in config.order:
+            masks = timed("qk_s", lambda: compress_qk(adapter=adapter, cov=(cov_q, cov_k),
+                                                     keep_ratios=keep, target_layers=target))
+            rotary_masks.extend(masks or [])
+        if "vo" in config.order:
+            timed("vo_s", lambda: compress_vo(adapter=adapter, cov=cov_x, keep_ratios=keep,
+                                              target_layers=target))
+        del cov_mlp, cov_q, cov_k, cov_x
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    D.barrier()   # every owner has written its layer files
+    tokens = config.calib_size * config.seq_len
+    adapter.metrics.update({**timings, "calib_tokens_per_s": tokens / max(timings["calibration_s"], 1e-9),
+                            "compress_s_per_layer": (timings["mlp_s"] + timings["qk_s"]
+                                                     + timings["vo_s"]) / n_layers,
+                            "world_size": D.world_size()})
+    if not is_root:
+        return None
+
+    suffixes = [s for s in ("mlp", "qk", "vo") if s in config.order]
+    adapter.convert_model(saved_layers_dir=config.temp_storage_dir, suffixes=suffixes)
+    adapter.patch_config()
+    save_compressed_model(adapter, rotary_masks=rotary_masks if "qk" in config.order else None,
+                          save_dir=save_dir, source_model_name=config.model)
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    model, tokenizer = reload_compressed_model(save_dir, device=device)
+    adapter.model, adapter.tokenizer = model, tokenizer
+    ppl = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
+    adapter.metrics[f"ppl-{config.dataset}"] = ppl
+    adapter.save_metrics()
+    logger.info(f"Compressed (PPL): {ppl}")
+    logger.info(f"calibration {timings['calibration_s']:.2f}s "
+                f"({adapter.metrics['calib_tokens_per_s']:.0f} tok/s), compress "
+                f"{adapter.metrics['compress_s_per_layer']:.3f} s/layer")
+    return ppl
+
+
+if __name__ == "__main__":
+    main()

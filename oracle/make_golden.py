@@ -66,6 +66,12 @@ def f64(t: torch.Tensor) -> np.ndarray:
     return t.detach().to(torch.float64).cpu().numpy()
 
 
+def bf16_bits(t: torch.Tensor) -> np.ndarray:
+    """bf16 tensor -> uint16 bit patterns (lossless, half the size of fp32 fixtures)."""
+    assert t.dtype == torch.bfloat16
+    return t.detach().contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
 def shaped_gram(rng: np.random.Generator, t: int, n: int, spread: float = 1.0):
     """Activations with a per-channel scale spread so score gaps sit far above rounding noise."""
     x = rng.standard_normal((t, n)) * np.exp(spread * rng.standard_normal(n))
@@ -154,7 +160,7 @@ def golden_qk(ref, rng):
 
 def golden_vo(ref, rng):
     out = {}
-    d, hd, rank = 48, 16, 10
+    d, hd, rank = 64, 32, 20
     _, c = shaped_gram(rng, 400, d, spread=0.7)
     root = ref.cu.sqrt_M(torch.tensor(c), ridge_lambda=1e-5)
     root_inv = torch.linalg.inv(root)
@@ -181,8 +187,8 @@ def golden_pipeline(ref, tag: str, n_kv: int, qwen: bool = False):
     from transformers import AutoModelForCausalLM, LlamaConfig, Qwen3Config
 
     torch.manual_seed(0)
-    kw = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4,
-              num_key_value_heads=n_kv, head_dim=16, vocab_size=160, max_position_embeddings=256,
+    kw = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=4,
+              num_key_value_heads=n_kv, head_dim=32, vocab_size=160, max_position_embeddings=256,
               tie_word_embeddings=False)
     cfg = Qwen3Config(**kw) if qwen else LlamaConfig(**kw)
     model = AutoModelForCausalLM.from_config(cfg).to(torch.bfloat16).eval()
@@ -190,10 +196,10 @@ def golden_pipeline(ref, tag: str, n_kv: int, qwen: bool = False):
     g = torch.Generator().manual_seed(7)
     with torch.no_grad():
         for blk in model.model.layers:
-            blk.mlp.up_proj.weight.mul_(torch.exp(0.6 * torch.randn(128, 1, generator=g)).to(torch.bfloat16))
-            blk.self_attn.q_proj.weight.mul_(torch.exp(0.6 * torch.randn(64, 1, generator=g)).to(torch.bfloat16))
-            blk.self_attn.k_proj.weight.mul_(torch.exp(0.6 * torch.randn(16 * n_kv, 1, generator=g)).to(torch.bfloat16))
-            blk.input_layernorm.weight.mul_(torch.exp(0.5 * torch.randn(64, generator=g)).to(torch.bfloat16))
+            blk.mlp.up_proj.weight.mul_(torch.exp(0.6 * torch.randn(256, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn.q_proj.weight.mul_(torch.exp(0.6 * torch.randn(128, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn.k_proj.weight.mul_(torch.exp(0.6 * torch.randn(32 * n_kv, 1, generator=g)).to(torch.bfloat16))
+            blk.input_layernorm.weight.mul_(torch.exp(0.5 * torch.randn(128, generator=g)).to(torch.bfloat16))
     adapter = ref.ma.ModelAdapter.from_model(model, tokenizer=None)
     tmp = tempfile.mkdtemp(prefix="mg_golden_")
     adapter.config = ref.cc.CompressionConfig(
@@ -237,21 +243,21 @@ def golden_pipeline(ref, tag: str, n_kv: int, qwen: bool = False):
     ref.vo.compress_vo(adapter, cov_x, keep, target_layers=[0, 1, 2])
 
     out = {"tokens": tokens.numpy(), "bi": np.array(bi), "keep": np.array(keep),
-           "cfg": np.array([64, 128, 3, 4, n_kv, 16, 160, int(qwen)])}
+           "cfg": np.array([128, 256, 3, 4, n_kv, 32, 160, int(qwen)])}
     for k, v in model.state_dict().items():
-        out["w:" + k] = v.float().numpy()
+        out["w:" + k] = bf16_bits(v)            # the model is bf16: store the exact bit patterns
     for i in range(3):
         out[f"cov_mlp{i}"], out[f"cov_q{i}"] = f64(cov_mlp[i]), f64(cov_q[i])
         out[f"cov_k{i}"], out[f"cov_x{i}"] = f64(cov_k[i]), f64(cov_x[i])
         for name in cap:
-            out[f"{name}{i}"] = torch.stack(cap[name][i]).float().numpy()     # [batches, B, T, n]
+            out[f"{name}{i}"] = bf16_bits(torch.stack(cap[name][i]))          # [batches, B, T, n]
         out[f"mask{i}"] = masks[i].numpy()
         for suf in ("mlp", "qk", "vo"):
             d = torch.load(os.path.join(tmp, f"layer_{i}_{suf}"))
             for k, v in d.items():
                 out[f"L{i}_{suf}_{k}"] = v.float().numpy()
     for b, hs in enumerate(hs_cap):
-        out[f"hidden{b}"] = torch.stack(hs).float().numpy()                    # [L+1, B, T, D]
+        out[f"hidden{b}"] = bf16_bits(torch.stack(hs))                         # [L+1, B, T, D]
     np.savez_compressed(OUT / f"pipeline_{tag}.npz", **out)
 
 

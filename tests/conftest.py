@@ -36,7 +36,10 @@ def golden():
 
     def load(name):
         if name not in cache:
-            cache[name] = dict(np.load(GOLDEN / f"{name}.npz"))
+            raw = dict(np.load(GOLDEN / f"{name}.npz"))
+            # bf16 tensors are stored as uint16 bit patterns: widen to float32 (exact)
+            cache[name] = {k: ((v.astype(np.uint32) << 16).view(np.float32) if v.dtype == np.uint16 else v)
+                           for k, v in raw.items()}
         return cache[name]
 
     return load

@@ -1,0 +1,301 @@
+"""GPU parity: every kernel of libmodegpt_b200 against the CPU oracle (fp64) on seeded inputs.
+
+Tolerances: statistics and compressed weights <= 1e-3 relative Frobenius (north_star); indices and
+gathers bit-exact.  Weight outputs are bf16 like the reference's, so two correct implementations
+can differ by a bf16 ulp on individual elements: those comparisons are made against the oracle's
+bf16-ROUNDED result and additionally require > 97 % of elements to be identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import modegpt_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from modegpt_b200 import ops as _ops
+
+    return _ops
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def shaped(t, n, seed, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(t, n, generator=g) * torch.exp(spread * torch.randn(n, generator=g))
+    return x.bfloat16()
+
+
+def upper(a):
+    return np.triu(np.asarray(a))
+
+
+# ----------------------------------------------------------------------------- statistics
+@pytest.mark.parametrize("T,n", [(1, 8), (7, 64), (64, 256), (1000, 512), (300, 328), (2048, 1096),
+                                 (4096, 4096)])
+def test_syrk_matches_oracle(ops, T, n):
+    x = shaped(T, n, seed=T + n)
+    c = torch.zeros(n, n, device=DEV)
+    ops.syrk_(c, x.to(DEV))
+    ref = O.gram_rows(x.float().numpy())
+    assert rel(upper(c.cpu().numpy()), upper(ref)) < 1e-3
+
+
+def test_syrk_accumulates_and_overwrites(ops):
+    x, y = shaped(500, 384, 1).to(DEV), shaped(260, 384, 2).to(DEV)
+    c = torch.zeros(384, 384, device=DEV)
+    ops.syrk_(c, x)
+    ops.syrk_(c, y)
+    ref = O.gram_rows(x.float().cpu().numpy()) + O.gram_rows(y.float().cpu().numpy())
+    assert rel(upper(c.cpu().numpy()), upper(ref)) < 1e-5
+    ops.syrk_(c, y, alpha=0.5, accumulate=False)
+    assert rel(upper(c.cpu().numpy()), upper(0.5 * O.gram_rows(y.float().cpu().numpy()))) < 1e-5
+
+
+def test_syrk_strided_activation_view(ops):
+    """[B, T, n] activations and row-strided views are consumed without a copy."""
+    big = shaped(512, 640, 3).to(DEV)
+    view = big[:, :256]                      # ld = 640
+    c = torch.zeros(256, 256, device=DEV)
+    ops.syrk_(c, view.view(2, 256, 256) if view.is_contiguous() else view)
+    assert rel(upper(c.cpu().numpy()), upper(O.gram_rows(view.float().cpu().numpy()))) < 1e-5
+
+
+def test_finalize_sym(ops):
+    c = torch.randn(333, 333, device=DEV)
+    want = np.triu(c.cpu().numpy()) * 0.25
+    want = want + np.triu(want, 1).T
+    ops.finalize_sym_(c, 0.25)
+    np.testing.assert_array_equal(c.cpu().numpy(), want.astype(np.float32))
+
+
+@pytest.mark.parametrize("T,H,hd", [(777, 4, 128), (1024, 12, 64), (130, 8, 32), (4096, 32, 128)])
+def test_syrk_heads_matches_oracle(ops, T, H, hd):
+    x = shaped(T, H * hd, seed=hd + H)
+    c = torch.zeros(H, hd, hd, device=DEV)
+    ops.syrk_heads_(c, x.to(DEV))
+    assert rel(c.cpu().numpy(), O.gram_heads(x.float().numpy(), H, hd)) < 1e-3
+
+
+@pytest.mark.parametrize("B,T,d", [(2, 96, 64), (3, 128, 776), (2, 256, 4096)])
+def test_bi_cosine_matches_oracle(ops, B, T, d):
+    g = torch.Generator().manual_seed(d)
+    a = torch.randn(B, T, d, generator=g).bfloat16()
+    b = (a.float() + 0.4 * torch.randn(B, T, d, generator=g)).bfloat16()
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.bi_cosine_(acc, a.to(DEV), b.to(DEV))
+    want = O.bi_batch(a.float().numpy(), b.float().numpy()) * T   # oracle returns the mean over T
+    assert abs(acc.item() - want) / want < 1e-6
+
+
+def test_wrong_dtype_and_shape_raise(ops):
+    with pytest.raises(TypeError):
+        ops.syrk_(torch.zeros(8, 8, device=DEV), torch.zeros(4, 8, device=DEV))        # fp32 X
+    with pytest.raises(ValueError):
+        ops.syrk_(torch.zeros(8, 16, device=DEV), torch.zeros(4, 8, device=DEV).bfloat16())
+    from modegpt_b200._lib import MgError
+    with pytest.raises(MgError):   # ld not a multiple of 8 elements: TMA cannot address it
+        ops.syrk_(torch.zeros(12, 12, device=DEV), torch.zeros(4, 13, device=DEV).bfloat16()[:, :12])
+
+
+# ----------------------------------------------------------------------------- golden: statistics
+@pytest.mark.parametrize("tag", ["llama_mha", "llama_gqa", "qwen3_gqa"])
+def test_statistics_on_reference_activations(ops, golden, tag):
+    """The exact tensors the reference's hooks saw -> our kernels -> the reference's C (fp64)."""
+    g = golden(f"pipeline_{tag}")
+    d, d_int, L, H, KV, hd, _, _ = (int(x) for x in g["cfg"])
+    n_texts = g["tokens"].shape[0]
+    scale = 1.0 / (n_texts * 2048)
+    for l in range(L):
+        for name, n, key in (("mlp_in", d_int, "cov_mlp"), ("ln_out", d, "cov_x")):
+            c = torch.zeros(n, n, device=DEV)
+            for batch in g[f"{name}{l}"]:
+                ops.syrk_(c, torch.tensor(batch, device=DEV).bfloat16())
+            ops.finalize_sym_(c, scale)
+            assert rel(c.cpu().numpy(), g[f"{key}{l}"]) < 1e-3
+        for name, heads, key in (("q_out", H, "cov_q"), ("k_out", KV, "cov_k")):
+            c = torch.zeros(heads, hd, hd, device=DEV)
+            for batch in g[f"{name}{l}"]:
+                ops.syrk_heads_(c, torch.tensor(batch, device=DEV).bfloat16())
+            ops.scale_(c, scale)
+            assert rel(c.cpu().numpy(), g[f"{key}{l}"]) < 1e-3
+    acc = torch.zeros(L, dtype=torch.float64, device=DEV)
+    T = g["tokens"].shape[1]
+    for b in range(2):
+        hs = torch.tensor(g[f"hidden{b}"], device=DEV).bfloat16()
+        for l in range(L):
+            ops.bi_cosine_(acc[l:l + 1], hs[l], hs[l + 1])
+    np.testing.assert_allclose((acc / T / n_texts).cpu().numpy(), g["bi"], rtol=1e-6)
+
+
+# ----------------------------------------------------------------------------- type I
+def _bf16_close(ours: torch.Tensor, want: np.ndarray, frac=0.97, tol=1e-3):
+    got = ours.float().cpu().numpy()
+    assert got.shape == want.shape
+    assert rel(got, want) < tol
+    assert np.mean(got == want) > frac
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_type1_against_reference_golden(ops, golden, tag):
+    g = golden("mlp")
+    keep, ridge = g[f"{tag}_params"]
+    c = torch.tensor(g[f"{tag}_c"], device=DEV, dtype=torch.float32)
+    scores = ops.ridge_scores(c, float(np.float32(ridge)))
+    assert rel(scores.cpu().numpy(), g[f"{tag}_scores"]) < 1e-4
+    rank = int(g[f"{tag}_rank"])
+    idx = ops.select_k(scores, rank)
+    _, ref_idx, _ = O.nystrom_mlp(g[f"{tag}_wu"], g[f"{tag}_wg"], g[f"{tag}_wd"], g[f"{tag}_c"], keep, ridge)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)
+    wu = torch.tensor(g[f"{tag}_wu"], device=DEV).bfloat16()
+    wd = torch.tensor(g[f"{tag}_wd"], device=DEV).bfloat16()
+    np.testing.assert_array_equal(ops.gather_rows(wu, idx).float().cpu().numpy(), g[f"{tag}_up"])
+    _bf16_close(ops.nystrom_down(c, idx, wd), g[f"{tag}_down"].astype(np.float32))
+
+
+@pytest.mark.parametrize("n,d,keep,ridge,spread", [(130, 24, 0.5, 1e-2, 1.0), (512, 128, 0.75, 1e-4, 1.0),
+                                                   (1000, 200, 0.66, 1e-4, 0.3), (1536, 256, 0.9, 1e-2, 1.5)])
+def test_type1_matches_oracle(ops, n, d, keep, ridge, spread):
+    x = shaped(4 * n, n, seed=n, spread=spread).double().numpy()
+    c64 = x.T @ x / x.shape[0]
+    c = torch.tensor(c64, device=DEV, dtype=torch.float32)
+    c64 = c.double().cpu().numpy()                      # the oracle sees the same fp32-rounded C
+    g = torch.Generator().manual_seed(n)
+    wu = (torch.randn(n, d, generator=g) * 0.05).bfloat16()
+    wd = (torch.randn(d, n, generator=g) * 0.05).bfloat16()
+    want, ref_idx, rank = O.nystrom_mlp(wu.float().numpy(), None, wd.float().numpy(), c64, keep, ridge)
+    scores = ops.ridge_scores(c, float(np.float32(ridge)))
+    ref_scores = O.ridge_scores(c64, ridge)
+    assert rel(scores.cpu().numpy(), ref_scores) < 1e-4
+    idx = ops.select_k(scores, rank).cpu().numpy()
+    # indices must agree wherever the score gap to the selection threshold exceeds fp32 noise
+    order = np.sort(ref_scores)
+    thr = 0.5 * (order[rank - 1] + order[rank]) if rank < n else np.inf
+    decisive = np.abs(ref_scores - thr) > 1e-5 * np.abs(thr)
+    sel, ref_sel = np.zeros(n, bool), np.zeros(n, bool)
+    sel[idx], ref_sel[ref_idx] = True, True
+    assert np.array_equal(sel[decisive], ref_sel[decisive])
+    assert np.all(np.diff(idx) > 0)
+    if np.array_equal(idx, ref_idx):
+        down = ops.nystrom_down(c, torch.tensor(idx, device=DEV), wd.to(DEV))
+        _bf16_close(down, want["down"])
+
+
+def test_select_k_edge_cases(ops):
+    s = torch.tensor([3.0, 1.0, 2.0, 1.0, 5.0, 1.0, -2.0, 0.0], device=DEV)
+    assert ops.select_k(s, 3).tolist() == [1, 6, 7]                 # ties resolve to the lower index
+    assert ops.select_k(s, 4).tolist() == [1, 3, 6, 7]
+    assert ops.select_k(s, 8).tolist() == list(range(8))
+    assert ops.select_k(s, 2, largest=True).tolist() == [0, 4]
+    big = torch.rand(30000, device=DEV)
+    want = torch.sort(torch.topk(big, 12345, largest=False).indices).values
+    assert torch.equal(ops.select_k(big, 12345), want)
+
+
+def test_not_positive_definite_is_reported(ops):
+    c = torch.eye(300, device=DEV)
+    c[200, 200] = -4.0
+    with pytest.raises(ops.NotPositiveDefinite) as e:
+        ops.ridge_scores(c, 1e-3)
+    assert e.value.pivot == 201
+
+
+# ----------------------------------------------------------------------------- type II
+def test_type2_against_reference_golden(ops, golden):
+    g = golden("qk")
+    cq = torch.tensor(g["gqa_cq"], device=DEV, dtype=torch.float32)
+    ck = torch.tensor(g["gqa_ck"][None], device=DEV, dtype=torch.float32)
+    mask = ops.qk_select(cq, ck, int(g["gqa_rank"]), 0, 1e-4, float(g["gqa_ridge"]))
+    np.testing.assert_array_equal(mask.cpu().numpy()[0], g["gqa_mask"])
+    hd, d = g["gqa_wq"].shape[1:]
+    wq = torch.tensor(g["gqa_wq"].reshape(-1, d), device=DEV).bfloat16()
+    wk = torch.tensor(g["gqa_wk"].reshape(-1, d), device=DEV).bfloat16()
+    q = ops.gather_head_rows(wq, mask, 3, 3, hd).float().cpu().numpy()
+    np.testing.assert_array_equal(q.reshape(3, -1, d), g["gqa_q"])
+    np.testing.assert_array_equal(ops.gather_head_rows(wk, mask, 1, 1, hd).float().cpu().numpy(), g["gqa_k"])
+    c1 = torch.tensor(g["mha_cq"][None], device=DEV, dtype=torch.float32)
+    c2 = torch.tensor(g["mha_ck"][None], device=DEV, dtype=torch.float32)
+    m = ops.qk_select(c1, c2, int(g["mha_rank"]), 0, 1e-4, 1e-4)
+    np.testing.assert_array_equal(m.cpu().numpy()[0], g["mha_mask"])
+    m = ops.qk_select(c1, c2, int(g["opt_rank"]), 1, 1e-4, 1e-4)
+    np.testing.assert_array_equal(g["opt_wq"][m.cpu().numpy()[0]], g["opt_q"])
+
+
+@pytest.mark.parametrize("H,KV,hd,r,mode,arch", [(8, 2, 128, 96, 0, "llama"), (4, 4, 64, 40, 0, "llama"),
+                                                 (12, 12, 64, 44, 1, "opt"), (6, 2, 32, 2, 0, "qwen3"),
+                                                 (4, 4, 128, 128, 0, "llama")])
+def test_type2_matches_oracle(ops, H, KV, hd, r, mode, arch):
+    cq = np.stack([O.gram_rows(shaped(300, hd, i).float().numpy()) / 300 for i in range(H)])
+    ck = np.stack([O.gram_rows(shaped(300, hd, 50 + i).float().numpy()) / 300 for i in range(KV)])
+    cq32, ck32 = cq.astype(np.float32), ck.astype(np.float32)
+    g = torch.Generator().manual_seed(7)
+    wq = torch.randn(H * hd, 96, generator=g).bfloat16()
+    wk = torch.randn(KV * hd, 96, generator=g).bfloat16()
+    want, ref_mask = O.qk_layer(wq.float().numpy(), wk.float().numpy(), cq32.astype(np.float64),
+                                ck32.astype(np.float64), H, KV, hd, r, arch, 1e-2)
+    ridge_k = 1e-2 if (mode == 0 and H != KV) else 1e-4
+    mask = ops.qk_select(torch.tensor(cq32, device=DEV), torch.tensor(ck32, device=DEV), r, mode, 1e-4, ridge_k)
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask)
+    np.testing.assert_array_equal(
+        ops.gather_head_rows(wq.to(DEV), mask, H, H // KV, hd).float().cpu().numpy(), want["q_proj"])
+    np.testing.assert_array_equal(
+        ops.gather_head_rows(wk.to(DEV), mask, KV, 1, hd).float().cpu().numpy(), want["k_proj"])
+
+
+# ----------------------------------------------------------------------------- type III
+def _vo_products(v, o, H, KV, r):
+    grp = H // KV
+    return [np.asarray(o[:, q * r:(q + 1) * r], np.float64) @ np.asarray(v[(q // grp) * r:(q // grp + 1) * r], np.float64)
+            for q in range(H)]
+
+
+def test_type3_against_reference_golden(ops, golden):
+    """compress_head (MHA) and compress_head_grouped (GQA) outputs of the reference itself."""
+    g = golden("vo")
+    hd, r = int(g["hd"]), int(g["rank"])
+    c = torch.tensor(g["c"], device=DEV, dtype=torch.float32)
+    wv = torch.tensor(g["mha_wv"], device=DEV).bfloat16()
+    wo = torch.tensor(g["mha_wo"], device=DEV).bfloat16()
+    v, o = ops.vo_compress(c, float(g["ridge"]), wv, wo, 2, 2, hd, r)
+    ours = _vo_products(v.float().cpu().numpy(), o.float().cpu().numpy(), 2, 2, r)
+    want = _vo_products(g["mha_v"], g["mha_o"], 2, 2, r)
+    for a, b in zip(ours, want):
+        assert rel(a, b) < 5e-3          # both factors are bf16-rounded on our side
+    v, o = ops.vo_compress(c, float(g["ridge"]), wv[:hd].contiguous(), wo, 2, 1, hd, r)
+    ours = _vo_products(v.float().cpu().numpy(), o.float().cpu().numpy(), 2, 1, r)
+    want = _vo_products(g["gqa_v"], g["gqa_o"], 2, 1, r)
+    for a, b in zip(ours, want):
+        assert rel(a, b) < 5e-3
+
+
+@pytest.mark.parametrize("d,H,KV,hd,r", [(256, 4, 4, 64, 40), (512, 8, 2, 64, 48), (512, 4, 4, 128, 96),
+                                         (384, 6, 3, 32, 20), (256, 2, 2, 128, 128)])
+def test_type3_matches_oracle(ops, d, H, KV, hd, r):
+    x = shaped(4 * d, d, seed=d + hd, spread=0.6).double().numpy()
+    c = torch.tensor(x.T @ x / x.shape[0], device=DEV, dtype=torch.float32)
+    g = torch.Generator().manual_seed(d)
+    wv = (torch.randn(KV * hd, d, generator=g) * 0.05).bfloat16()
+    wo = (torch.randn(d, H * hd, generator=g) * 0.05).bfloat16()
+    v, o = ops.vo_compress(c, 1e-5, wv.to(DEV), wo.to(DEV), H, KV, hd, r)
+    _, v64, o64 = O.vo_layer(wv.float().numpy(), wo.float().numpy(), c.double().cpu().numpy(), H, KV, hd, r, 1e-5)
+    assert v.shape == (KV * r, d) and o.shape == (d, H * r)
+    ours = _vo_products(v.float().cpu().numpy(), o.float().cpu().numpy(), H, KV, r)
+    want = _vo_products(O.to_bf16(v64), O.to_bf16(o64), H, KV, r)
+    exact = _vo_products(v64, o64, H, KV, r)
+    for a, b, e in zip(ours, want, exact):
+        # sign-free comparison: O'V' per head is unique.  The bound is the error the reference's own
+        # bf16 rounding of the two factors makes against exact arithmetic.
+        assert rel(a, e) < 1.5 * rel(b, e) + 1e-4
+    # sign-aligned factors, element-wise
+    grp = H // KV
+    for h in range(KV):
+        vo, vr = v.float().cpu().numpy()[h * r:(h + 1) * r], v64[h * r:(h + 1) * r]
+        sgn = np.sign(np.sum(vo * vr, axis=1))
+        assert rel(vo * sgn[:, None], vr) < 5e-3
