@@ -70,12 +70,15 @@ def _calibrate_model(adapter: ModelAdapter, n_samples: int, batch_size: int,
     adapter.register_bi_hooks(bi_batch, handles)
 
     model.eval()
+    # the LM head is not on the statistics path: run the decoder stack only (its final norm, whose
+    # output closes the last Block-Influence pair, is part of it)
+    body = getattr(model, "model", model)
     n_texts = 0
     try:
         for batch in D.shard_batches(adapter.calibs):
             batch = batch.to(device, non_blocking=True)
             n_texts += len(batch)
-            model(batch, use_cache=False)
+            body(batch, use_cache=False)
             # sum over the batch, mean over positions (src/calibration.py:122-124)
             bi_total += bi_batch / batch.shape[1]
             bi_batch.zero_()
