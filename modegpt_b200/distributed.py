@@ -15,8 +15,12 @@ import torch
 import torch.distributed as dist
 
 
+_force_single = False   # tests: run the single-process semantics inside an initialised group
+
+
 def is_distributed() -> bool:
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return (not _force_single and dist.is_available() and dist.is_initialized()
+            and dist.get_world_size() > 1)
 
 
 def rank() -> int:
