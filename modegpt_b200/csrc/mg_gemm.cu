@@ -500,6 +500,7 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.kblocks = static_cast<int>((a.K + BK - 1) / BK);
   int ksplit = a.ksplit;
   if (ksplit <= 0) {
+    const int at_least = ksplit < 0 ? -ksplit : 1;
     ksplit = 1;
     if (a.epi == EPI_ADD && kp.ntiles < device_sm_count()) {
       ksplit = (2 * device_sm_count() + kp.ntiles - 1) / kp.ntiles;
@@ -508,6 +509,7 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
       if (ksplit > max_split) ksplit = max_split;
       if (ksplit < 1) ksplit = 1;
     }
+    if (ksplit < at_least) ksplit = at_least;
   }
   if (ksplit > 1 && a.epi != EPI_ADD) return -9;
   if (ksplit > kp.kblocks) ksplit = kp.kblocks;

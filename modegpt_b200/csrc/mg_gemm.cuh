@@ -45,7 +45,7 @@ struct GemmArgs {
   int tiles;   // TileSet
   int epi;     // EpiOp
   int hd;      // TILES_DIAG: block size (divides 128)
-  int ksplit;  // >= 1; > 1 requires EPI_ADD (atomics); 0 = choose automatically
+  int ksplit;  // >= 1; > 1 requires EPI_ADD; 0 = choose automatically; < 0 = automatic, at least -ksplit
   // B is lower-triangular in (k, n): B[k, n] == 0 for n > k, so an N tile starting at column c0
   // only needs k >= c0 (used by the blocked triangular inverse).
   int klo_from_n;
@@ -55,5 +55,16 @@ struct GemmArgs {
 int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream);
 
 int device_sm_count();
+
+// The tensor core aligns and TRUNCATES when it accumulates in fp32, which biases long sums of
+// same-sign products (a Gram diagonal) by about 2^-24 per 16 accumulated rows.  Statistics
+// therefore accumulate at most kMaxAccumRows rows in TMEM per run and add the runs in L2 with
+// round-to-nearest (the reduce-add epilogue): a K segmentation, not extra work.  Measured on
+// B200 at n = 11008: one 16384-row run 2.7e-5 relative on the diagonal, 4096-row runs 1.2e-5 but
+// 10 % slower (8x the epilogues) — so the cap only bounds the bias of very long calls.
+constexpr int64_t kMaxAccumRows = 32768;
+inline int segments_for(int64_t rows) {
+  return static_cast<int>((rows + kMaxAccumRows - 1) / kMaxAccumRows);
+}
 
 }  // namespace mg

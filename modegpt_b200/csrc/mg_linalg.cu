@@ -5,8 +5,12 @@
 #include "mg_linalg.cuh"
 
 #include "mg_gemm.cuh"
+#include "mg_prof.cuh"
 
 namespace mg {
+
+__device__ long long g_dbg_clk[64];
+#define MG_CLK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_dbg_clk[slot] = clock64(); } while (0)
 
 namespace {
 
@@ -91,18 +95,18 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 //   (2) one thread per remaining column does the 32-step forward substitution,
 //   (3) all threads apply the rank-32 update to the trailing part of the block.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDiagLd = kNB + 1;
+constexpr int kDiagLd = kNB + 2;   // even: rows stay 16-byte aligned for double2 accesses
 constexpr int kPotrfThreads = 512;
-constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 32);
+constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 64);
 
 __global__ void __launch_bounds__(kPotrfThreads, 1)
     potrf128_kernel(float* __restrict__ A, int64_t ld, int64_t j0, int nb,
                     float* __restrict__ t_fwd, float* __restrict__ t_bwd,
                     __nv_bfloat16* __restrict__ u_planes, __nv_bfloat16* __restrict__ l_planes,
                     int64_t ld_up, int64_t up_plane_stride, int* __restrict__ info) {
-  extern __shared__ double sm[];
-  double* a = sm;                     // [128][129], upper triangle live
-  double* invd = sm + kNB * kDiagLd;  // [32] reciprocal pivots of the current sub-panel
+  extern __shared__ __align__(16) double sm[];
+  double* a = sm;                     // [128][130], upper triangle live
+  double* invd = sm + kNB * kDiagLd;  // [32] reciprocal pivots of the current sub-panel, + [32] pivot row
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
 
@@ -112,64 +116,116 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
     if (i < nb && k < nb && i <= k) v = static_cast<double>(A[(j0 + i) * ld + (j0 + k)]);
     a[i * kDiagLd + k] = v;
   }
+  MG_CLK(0);
   __syncthreads();
+  MG_CLK(1);
 
   const int nsub = (nb + 31) / 32;
   for (int kb = 0; kb < nsub; ++kb) {
     const int c0 = kb * 32;
+    // (1) 32 x 32 diagonal block, one warp: lane i owns ROW i in registers; each step the scaled
+    //     pivot row goes through shared memory (broadcast reads) instead of 31 double shuffles
     if (warp == 0) {
-      double col[32];
+      double* urow = invd + 32;          // [32] scaled pivot row
+      double row[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) col[i] = (i <= lane) ? a[(c0 + i) * kDiagLd + c0 + lane] : 0.0;
+      for (int k = 0; k < 32; ++k) row[k] = (k >= lane) ? a[(c0 + lane) * kDiagLd + c0 + k] : 0.0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        double piv = __shfl_sync(0xffffffffu, col[j], j);
-        if (!(piv > 0.0)) {
-          if (lane == 0 && c0 + j < nb) atomicCAS(info, 0, static_cast<int>(j0 + c0 + j + 1));
-          piv = 1e-30;
-        }
-        const double d = sqrt(piv);
-        const double inv = 1.0 / d;
-        const double ujk = (lane > j) ? col[j] * inv : (lane == j ? d : 0.0);
-        col[j] = ujk;
-        if (lane == j) invd[j] = inv;
+        if (lane == j) {
+          double piv = row[j];
+          if (!(piv > 0.0)) {
+            if (c0 + j < nb) atomicCAS(info, 0, static_cast<int>(j0 + c0 + j + 1));
+            piv = 1e-30;
+          }
+          const double inv = rsqrt(piv);
+          invd[j] = inv;
+          row[j] = piv * inv;
 #pragma unroll
-        for (int i = j + 1; i < 32; ++i) {
-          const double uji = __shfl_sync(0xffffffffu, ujk, i);
-          col[i] -= uji * ujk;  // entries with i > lane are never read
+          for (int k = j + 1; k < 32; ++k) row[k] *= inv;
+#pragma unroll
+          for (int k = j; k < 32; ++k) urow[k] = row[k];
         }
+        __syncwarp();
+        if (lane > j) {
+          const double mult = urow[lane];
+#pragma unroll
+          for (int k = j + 1; k < 32; ++k) row[k] = fma(-mult, urow[k], row[k]);
+        }
+        __syncwarp();
       }
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i <= lane) a[(c0 + i) * kDiagLd + c0 + lane] = col[i];
+      for (int k = 0; k < 32; ++k)
+        if (k >= lane) a[(c0 + lane) * kDiagLd + c0 + k] = row[k];
     }
     __syncthreads();
+    MG_CLK(2 + 3 * kb);
+    // (2) block row: forward substitution, a quad of lanes per column (lane `part` owns 8 rows)
     const int rest = kNB - c0 - 32;  // columns right of the sub-panel (padding included)
-    if (t < rest) {
-      const int k = c0 + 32 + t;
-      double x[32];
+    {
+      const int cl = t >> 2, part = t & 3;
+      const int quad_base = lane & ~3;
+      const bool active = cl < rest;           // rest is a multiple of 32: warps are uniform
+      const int k = c0 + 32 + cl;
+      double r[8];
+      if (active) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        double s = a[(c0 + i) * kDiagLd + k];
+        for (int i = 0; i < 8; ++i) r[i] = a[(c0 + part * 8 + i) * kDiagLd + k];
 #pragma unroll
-        for (int m = 0; m < i; ++m) s -= a[(c0 + m) * kDiagLd + c0 + i] * x[m];
-        x[i] = s * invd[i];
+        for (int i = 0; i < 32; ++i) {
+          const int owner = i >> 3, li = i & 7;
+          double x = r[li] * invd[i];
+          x = __shfl_sync(0xffffffffu, x, quad_base | owner);
+          if (part == owner) r[li] = x;
+          // pivot-row entries U[c0+i][c0 + part*8 .. +8): only the lanes that still have rows
+          // below row i need them
+          if (part * 8 + 7 > i) {
+            const double2* tp = reinterpret_cast<const double2*>(a + (c0 + i) * kDiagLd + c0 + part * 8);
+            const double2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+            const double tv[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
+#pragma unroll
+            for (int l = 0; l < 8; ++l)
+              if (part * 8 + l > i) r[l] = fma(-tv[l], x, r[l]);
+          }
+        }
       }
+      __syncthreads();   // every read of the old block row is done
+      if (active) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) a[(c0 + i) * kDiagLd + k] = x[i];
+        for (int i = 0; i < 8; ++i) a[(c0 + part * 8 + i) * kDiagLd + k] = r[i];
+      }
     }
     __syncthreads();
-    // rank-32 update of the trailing upper triangle
-    for (int e = t; e < rest * rest; e += kPotrfThreads) {
-      const int ii = e / rest, kk = e - ii * rest;
-      if (ii > kk) continue;
-      const int i = c0 + 32 + ii, k = c0 + 32 + kk;
-      double s = 0.0;
-#pragma unroll 8
-      for (int m = 0; m < 32; ++m) s += a[(c0 + m) * kDiagLd + i] * a[(c0 + m) * kDiagLd + k];
-      a[i * kDiagLd + k] -= s;
+    MG_CLK(3 + 3 * kb);
+    // (3) rank-32 update of the trailing upper triangle, 4 x 4 register tiles
+    {
+      const int nt = rest / 4;       // rest is a multiple of 32
+      for (int e = t; e < nt * nt; e += kPotrfThreads) {
+        const int ti = e / nt, tk = e - ti * nt;
+        if (ti > tk) continue;
+        const int i0 = c0 + 32 + 4 * ti, k0 = c0 + 32 + 4 * tk;
+        double acc[4][4] = {};
+#pragma unroll 4
+        for (int m = 0; m < 32; ++m) {
+          const double2* pi = reinterpret_cast<const double2*>(a + (c0 + m) * kDiagLd + i0);
+          const double2* pk = reinterpret_cast<const double2*>(a + (c0 + m) * kDiagLd + k0);
+          const double2 i01 = pi[0], i23 = pi[1], k01 = pk[0], k23 = pk[1];
+          const double ui[4] = {i01.x, i01.y, i23.x, i23.y};
+          const double uk[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fma(ui[x], uk[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+            if (i0 + x <= k0 + y) a[(i0 + x) * kDiagLd + k0 + y] -= acc[x][y];
+      }
     }
     __syncthreads();
+    MG_CLK(4 + 3 * kb);
   }
 
   // ---- outputs
@@ -197,6 +253,7 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
       }
     }
   }
+  MG_CLK(19);
   // backward block: T'[m'][i'] = U[nb-1-i'][nb-1-m'] for m' <= i' < nb; identity beyond
   for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
     const int mp = e >> 7, ip = e & 127;
@@ -205,28 +262,65 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
       x = (mp <= ip) ? static_cast<float>(a[(nb - 1 - ip) * kDiagLd + (nb - 1 - mp)]) : 0.f;
     t_bwd[mp * kTLd + ip] = x;
   }
+  MG_CLK(20);
 }
 
 // ---------------------------------------------------------------------------------------------
 // trsm128: forward substitution with a compact lower-in-(m,i) block T (x_i = (b_i - sum_{m<i}
-// T[m][i] x_m) / T[i][i]), one thread per right-hand-side column, 32-row chunks held in
-// registers, earlier chunks' solutions parked in shared memory.  `reversed` maps chunk row i' to
+// T[m][i] x_m) / T[i][i]).  Four adjacent lanes (a quad) share one right-hand-side column: within
+// every 32-row chunk lane `part` owns rows part*8 .. part*8+7 in registers; solved rows are parked
+// in shared memory (xs[col][row], float4-readable) for the later chunks, and inside a chunk the
+// freshly solved value is broadcast through the quad by shuffle.  `reversed` maps chunk row i' to
 // matrix row nb-1-i' (that is how U x = b becomes a forward substitution).
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrsmThreads = 128;
-constexpr size_t kTrsmSmem = sizeof(float) * (kTBlock + kNB * kTrsmThreads + kNB);
+constexpr int kTrsmLanes = 8;                       // lanes sharing one column pair
+constexpr int kTrsmRows = 32 / kTrsmLanes;          // chunk rows owned by a lane (4)
+constexpr int kTrsmCpl = 2;                         // columns per lane: every T load feeds 8 FMAs
+constexpr int kTrsmThreads = 256;
+constexpr int kTrsmCols = kTrsmThreads / kTrsmLanes * kTrsmCpl;  // 64 columns per block
+constexpr int kXsLd = kNB + 4;                      // xs row stride (floats), 16-byte aligned rows
+constexpr size_t kTrsmSmem = sizeof(float) * (kTBlock + kTrsmCols * kXsLd + kNB);
 
-__global__ void __launch_bounds__(kTrsmThreads)
+__global__ void __launch_bounds__(kTrsmThreads, 2)
     trsm128_kernel(const float* __restrict__ tblock, int reversed, int nb,
                    const float* __restrict__ B, int64_t ldb, int64_t ncols, float alpha,
                    float* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ planes,
                    int64_t ldp, int64_t pstride, __nv_bfloat16* __restrict__ tplanes,
                    int64_t ldtp, int64_t tpstride, float* __restrict__ colsumsq) {
   extern __shared__ __align__(16) float smf[];
-  float* T = smf;                        // [128][132]
-  float* xs = smf + kTBlock;             // [128][kTrsmThreads]
-  float* invd = xs + kNB * kTrsmThreads; // [128]
+  float* T = smf;                          // [128][132]
+  float* xs = smf + kTBlock;               // [64 cols][132]: xs[col][row]
+  float* invd = xs + kTrsmCols * kXsLd;    // [128]
   const int tid = threadIdx.x;
+  const int pair_local = tid / kTrsmLanes, part = tid % kTrsmLanes;
+  const int lane = tid & 31;
+  const int group_base = lane & ~(kTrsmLanes - 1);
+  // the two columns of a lane are 32 apart so that a warp's 4 column pairs stay coalesced
+  const int cl0 = (pair_local / 4) * 8 + (pair_local % 4);
+  const int col_local[kTrsmCpl] = {cl0, cl0 + 4};
+  int64_t c[kTrsmCpl];
+  bool valid[kTrsmCpl];
+#pragma unroll
+  for (int q = 0; q < kTrsmCpl; ++q) {
+    c[q] = static_cast<int64_t>(blockIdx.x) * kTrsmCols + col_local[q];
+    valid[q] = c[q] < ncols;
+  }
+  const int nchunks = (nb + 31) / 32;
+
+  auto load_chunk = [&](int rb, float (&dst)[kTrsmCpl][kTrsmRows]) {
+#pragma unroll
+    for (int q = 0; q < kTrsmCpl; ++q)
+#pragma unroll
+      for (int i = 0; i < kTrsmRows; ++i) {
+        const int ip = rb * 32 + part * kTrsmRows + i;
+        const int row = reversed ? nb - 1 - ip : ip;
+        dst[q][i] = (valid[q] && ip < nb) ? B[static_cast<int64_t>(row) * ldb + c[q]] : 0.f;
+      }
+  };
+
+  float rn[kTrsmCpl][kTrsmRows];
+  load_chunk(0, rn);                       // in flight while the triangular block is staged
+  MG_CLK(32);
   {
     const float4* src = reinterpret_cast<const float4*>(tblock);
     float4* dst = reinterpret_cast<float4*>(T);
@@ -235,73 +329,128 @@ __global__ void __launch_bounds__(kTrsmThreads)
   __syncthreads();
   if (tid < kNB) invd[tid] = 1.f / T[tid * kTLd + tid];
   __syncthreads();
+  MG_CLK(33);
 
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * kTrsmThreads + tid;
-  const bool valid = c < ncols;
-  const int nchunks = (nb + 31) / 32;
-  float sumsq = 0.f;
+  float sumsq[kTrsmCpl] = {0.f, 0.f};
   for (int rb = 0; rb < nchunks; ++rb) {
-    float r[32];
+    float r[kTrsmCpl][kTrsmRows];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int ip = rb * 32 + i;
-      const int row = reversed ? nb - 1 - ip : ip;
-      r[i] = (valid && ip < nb) ? B[static_cast<int64_t>(row) * ldb + c] : 0.f;
-    }
+    for (int q = 0; q < kTrsmCpl; ++q)
+#pragma unroll
+      for (int i = 0; i < kTrsmRows; ++i) r[q][i] = rn[q][i];
+    if (rb + 1 < nchunks) load_chunk(rb + 1, rn);   // prefetch the next chunk's right-hand sides
+    const int ip0 = rb * 32 + part * kTrsmRows;     // first chunk-order row owned by this lane
+    MG_CLK(34 + 4 * rb);
+    // contributions of the chunks already solved
     for (int pb = 0; pb < rb; ++pb) {
-#pragma unroll 4
-      for (int m = 0; m < 32; ++m) {
-        const float xm = xs[(pb * 32 + m) * kTrsmThreads + tid];
-        const float4* t4 = reinterpret_cast<const float4*>(T + (pb * 32 + m) * kTLd + rb * 32);
+#pragma unroll 2
+      for (int m4 = 0; m4 < 32; m4 += 4) {
+        const float4 xa = *reinterpret_cast<const float4*>(xs + col_local[0] * kXsLd + pb * 32 + m4);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + col_local[1] * kXsLd + pb * 32 + m4);
+        const float xm[kTrsmCpl][4] = {{xa.x, xa.y, xa.z, xa.w}, {xb.x, xb.y, xb.z, xb.w}};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 tv = t4[q];
-          r[4 * q + 0] = fmaf(-tv.x, xm, r[4 * q + 0]);
-          r[4 * q + 1] = fmaf(-tv.y, xm, r[4 * q + 1]);
-          r[4 * q + 2] = fmaf(-tv.z, xm, r[4 * q + 2]);
-          r[4 * q + 3] = fmaf(-tv.w, xm, r[4 * q + 3]);
+        for (int mm = 0; mm < 4; ++mm) {
+          const float4 ta = *reinterpret_cast<const float4*>(T + (pb * 32 + m4 + mm) * kTLd + ip0);
+#pragma unroll
+          for (int q = 0; q < kTrsmCpl; ++q) {
+            r[q][0] = fmaf(-ta.x, xm[q][mm], r[q][0]);
+            r[q][1] = fmaf(-ta.y, xm[q][mm], r[q][1]);
+            r[q][2] = fmaf(-ta.z, xm[q][mm], r[q][2]);
+            r[q][3] = fmaf(-ta.w, xm[q][mm], r[q][3]);
+          }
         }
       }
     }
+    MG_CLK(35 + 4 * rb);
+    // the 32 x 32 diagonal chunk: row i is solved by its owner lane and broadcast in the group
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
+      const int owner = i / kTrsmRows, li = i % kTrsmRows;
       const int ip = rb * 32 + i;
-      const float x = r[i] * invd[ip];
-      r[i] = x;
-      xs[ip * kTrsmThreads + tid] = x;
-      const float* trow = T + ip * kTLd + rb * 32;
+      const float inv = invd[ip];
+      float x[kTrsmCpl];
 #pragma unroll
-      for (int i2 = i + 1; i2 < 32; ++i2) r[i2] = fmaf(-trow[i2], x, r[i2]);
+      for (int q = 0; q < kTrsmCpl; ++q) {
+        x[q] = __shfl_sync(0xffffffffu, r[q][li] * inv, group_base | owner);
+        if (part == owner) {
+          r[q][li] = x[q];
+          xs[col_local[q] * kXsLd + ip] = x[q];
+        }
+      }
+      if (part * kTrsmRows + kTrsmRows - 1 > i) {
+        const float4 ta = *reinterpret_cast<const float4*>(T + ip * kTLd + ip0);
+        const float tv[4] = {ta.x, ta.y, ta.z, ta.w};
+#pragma unroll
+        for (int l = 0; l < kTrsmRows; ++l)
+          if (part * kTrsmRows + l > i) {
+#pragma unroll
+            for (int q = 0; q < kTrsmCpl; ++q) r[q][l] = fmaf(-tv[l], x[q], r[q][l]);
+          }
+      }
     }
-    if (!valid) continue;
-    // ---- outputs of this chunk
+    __syncwarp();
+    MG_CLK(36 + 4 * rb);
+    // ---- outputs of this chunk (this lane's rows of its two columns)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int ip = rb * 32 + i;
-      if (ip >= nb) break;
-      const int row = reversed ? nb - 1 - ip : ip;
-      const float x = alpha * r[i];
-      sumsq = fmaf(x, x, sumsq);
-      if (X) X[static_cast<int64_t>(row) * ldx + c] = x;
-      if (planes || tplanes) {
-        __nv_bfloat16 h, m, l;
-        split3(x, h, m, l);
+    for (int q = 0; q < kTrsmCpl; ++q) {
+      if (!valid[q]) continue;
+      float xo[kTrsmRows];
+#pragma unroll
+      for (int i = 0; i < kTrsmRows; ++i) {
+        xo[i] = alpha * r[q][i];
+        if (ip0 + i < nb) sumsq[q] = fmaf(xo[i], xo[i], sumsq[q]);
+      }
+#pragma unroll
+      for (int i = 0; i < kTrsmRows; ++i) {
+        const int ip = ip0 + i;
+        if (ip >= nb) break;
+        const int row = reversed ? nb - 1 - ip : ip;
+        if (X) X[static_cast<int64_t>(row) * ldx + c[q]] = xo[i];
         if (planes) {
-          const int64_t o = static_cast<int64_t>(row) * ldp + c;
+          __nv_bfloat16 h, m, l;
+          split3(xo[i], h, m, l);
+          const int64_t o = static_cast<int64_t>(row) * ldp + c[q];
           planes[o] = h;
           planes[pstride + o] = m;
           planes[2 * pstride + o] = l;
         }
-        if (tplanes) {
-          const int64_t o = c * ldtp + row;
-          tplanes[o] = h;
-          tplanes[tpstride + o] = m;
-          tplanes[2 * tpstride + o] = l;
+      }
+      if (tplanes) {
+        __align__(8) __nv_bfloat16 hb[kTrsmRows], mb[kTrsmRows], lb[kTrsmRows];
+#pragma unroll
+        for (int i = 0; i < kTrsmRows; ++i) split3(xo[i], hb[i], mb[i], lb[i]);
+        const int64_t o = c[q] * ldtp + ip0;
+        const bool vec = !reversed && ip0 + kTrsmRows <= nb && ((o & 3) == 0) &&
+                         ((tpstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(tplanes) & 7) == 0);
+        if (vec) {   // 4 bf16 = one 8-byte store per plane
+          *reinterpret_cast<uint2*>(tplanes + o) = *reinterpret_cast<const uint2*>(hb);
+          *reinterpret_cast<uint2*>(tplanes + tpstride + o) = *reinterpret_cast<const uint2*>(mb);
+          *reinterpret_cast<uint2*>(tplanes + 2 * tpstride + o) = *reinterpret_cast<const uint2*>(lb);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kTrsmRows; ++i) {
+            const int ip = ip0 + i;
+            if (ip >= nb) break;
+            const int row = reversed ? nb - 1 - ip : ip;
+            const int64_t oo = c[q] * ldtp + row;
+            tplanes[oo] = hb[i];
+            tplanes[tpstride + oo] = mb[i];
+            tplanes[2 * tpstride + oo] = lb[i];
+          }
         }
       }
     }
   }
-  if (colsumsq && valid) atomicAdd(colsumsq + c, sumsq);
+  MG_CLK(50);
+  if (colsumsq) {
+#pragma unroll
+    for (int q = 0; q < kTrsmCpl; ++q) {
+      float v = sumsq[q];
+#pragma unroll
+      for (int o = 1; o < kTrsmLanes; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (part == 0 && valid[q]) atomicAdd(colsumsq + c[q], v);
+    }
+  }
 }
 
 }  // namespace
@@ -347,7 +496,7 @@ int trsm128(const float* tblock, bool reversed, int nb, const float* B, int64_t 
     if (e != cudaSuccess) return -1000 - static_cast<int>(e);
     attr_set = true;
   }
-  const unsigned grid = static_cast<unsigned>((ncols + kTrsmThreads - 1) / kTrsmThreads);
+  const unsigned grid = static_cast<unsigned>((ncols + kTrsmCols - 1) / kTrsmCols);
   trsm128_kernel<<<grid, kTrsmThreads, kTrsmSmem, s>>>(tblock, reversed ? 1 : 0, nb, B, ldb, ncols,
                                                        alpha, X, ldx, planes, ldp, pstride, tplanes,
                                                        ldtp, tpstride, colsumsq);
@@ -375,7 +524,7 @@ int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int
     const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
     float* tf = ws.t_fwd + pj * kTBlock;
     float* tb = ws.t_bwd + pj * kTBlock;
-    rc = potrf128(A, ld, j0, nb, tf, tb, ws.u_planes, ws.l_planes, np, pstride, info, s);
+    MG_TIMED(s, "chol.potrf128", rc = potrf128(A, ld, j0, nb, tf, tb, ws.u_planes, ws.l_planes, np, pstride, info, s));
     if (rc) return rc;
     const int64_t rest = n - j0 - nb;
     if (rest <= 0) break;
@@ -383,8 +532,8 @@ int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int
     float* a12 = A + j0 * ld + (j0 + nb);
     __nv_bfloat16* u12 = ws.u_planes + j0 * np + (j0 + nb);
     __nv_bfloat16* l21 = ws.l_planes ? ws.l_planes + (j0 + nb) * np + j0 : nullptr;
-    rc = trsm128(tf, false, nb, a12, ld, rest, 1.f, a12, ld, u12, np, pstride, l21, np, pstride,
-                 nullptr, s);
+    MG_TIMED(s, "chol.trsm128", rc = trsm128(tf, false, nb, a12, ld, rest, 1.f, a12, ld, u12, np, pstride,
+                                              l21, np, pstride, nullptr, s));
     if (rc) return rc;
     // trailing update on the upper triangle: A22 -= U12^T U12
     GemmArgs t{};
@@ -401,10 +550,16 @@ int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int
     t.tiles = TILES_UPPER;
     t.epi = EPI_ADD;
     t.ksplit = 1;
-    rc = gemm_tn_launch(t, s);
+    MG_TIMED(s, "chol.trailing_syrk", rc = gemm_tn_launch(t, s));
     if (rc) return rc;
   }
   return 0;
+}
+
+// debug: copy the phase timestamps written by block 0 / thread 0 of the last potrf128 (slots 0..20)
+// and trsm128 (slots 32..50) launches
+extern "C" int mg_debug_clocks(long long* out64) {
+  return cudaMemcpyFromSymbol(out64, g_dbg_clk, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace mg

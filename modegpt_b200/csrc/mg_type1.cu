@@ -12,6 +12,7 @@
 #include "../../include/modegpt_b200.h"
 #include "mg_gemm.cuh"
 #include "mg_linalg.cuh"
+#include "mg_prof.cuh"
 
 namespace {
 
@@ -332,9 +333,10 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
     const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
     const float* tf = w.chol.t_fwd + pj * mg::kTBlock;
     // diagonal block Y[jb, jb] = U_jj^-T (solve U_jj^T X = I)
-    if ((rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
-                          w.y_planes + j0 * np + j0, np, pstride, nullptr, 0, 0, scores + j0, s)))
-      return rc;
+    MG_TIMED(s, "trtri.diag_trsm", rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
+                                                    w.y_planes + j0 * np + j0, np, pstride, nullptr, 0, 0,
+                                                    scores + j0, s));
+    if (rc) return rc;
     if (j0 == 0) continue;
     // Tt[nb, j0] = U[0:j0, jb]^T * Y[0:j0, 0:j0]
     cudaMemsetAsync(w.tt, 0, sizeof(float) * kNB * np, s);
@@ -358,12 +360,15 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
     g.epi = mg::EPI_ADD;
     g.ksplit = 0;
     g.klo_from_n = 1;
-    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    MG_TIMED(s, "trtri.gemm1", rc = mg::gemm_tn_launch(g, s));
+    if (rc) return rc;
     // Y[jb, 0:j0] = -U_jj^-T Tt : planes + column sums of squares in one pass
-    if ((rc = mg::trsm128(tf, false, nb, w.tt, np, j0, -1.f, nullptr, 0, w.y_planes + j0 * np, np,
-                          pstride, nullptr, 0, 0, scores, s)))
-      return rc;
+    MG_TIMED(s, "trtri.row_trsm", rc = mg::trsm128(tf, false, nb, w.tt, np, j0, -1.f, nullptr, 0,
+                                                   w.y_planes + j0 * np, np, pstride, nullptr, 0, 0,
+                                                   scores, s));
+    if (rc) return rc;
   }
+  mg::Prof::get().report(s, "mg_ridge_scores_f32");
   return 0;
 }
 

@@ -1,0 +1,163 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties (the CPU oracle
+cannot finish these sizes in seconds): sub-block spot checks, linearity, symmetry, residuals of the
+linear systems, order statistics.  The checker is plain torch fp64 on the same device."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from modegpt_b200 import ops as _ops
+
+    return _ops
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300)).item()
+
+
+def activations(T, n, seed, spread=0.5):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn(T, n, device=DEV, generator=g)
+    return (x * torch.exp(spread * torch.randn(n, device=DEV, generator=g))).bfloat16()
+
+
+@pytest.fixture(scope="module")
+def c_mlp(ops):
+    """C_mlp of Llama-2-7B shape (n = 11008) from 16384 synthetic tokens, normalised + mirrored."""
+    n, T = 11008, 16384
+    x = activations(T, n, 0)
+    c = torch.zeros(n, n, device=DEV)
+    ops.syrk_(c, x[: T // 2])
+    ops.syrk_(c, x[T // 2:])
+    ops.finalize_sym_(c, 1.0 / T)
+    return c, x
+
+
+def test_syrk_7b_mlp_shape_blocks_linearity_symmetry(ops, c_mlp):
+    c, x = c_mlp
+    n, T = c.shape[0], x.shape[0]
+    xd = x.double()
+    for (r0, c0) in [(0, 0), (128, 10880), (5000, 5100), (10900, 10900), (3, 7777)]:
+        ref = xd[:, r0:r0 + 100].T @ xd[:, c0:c0 + 100] / T
+        # bar is 1e-3; the measured 1e-5..3e-5 is the tensor core's truncating fp32 accumulation
+        assert rel(c[r0:r0 + 100, c0:c0 + 100], ref) < 1e-4
+    assert torch.equal(c, c.T)                       # finalize mirrors exactly
+    whole = torch.zeros(n, n, device=DEV)            # two half-batches == one batch (fp32 order only)
+    ops.syrk_(whole, x)
+    ops.finalize_sym_(whole, 1.0 / T)
+    assert rel(whole, c) < 1e-4
+
+
+@pytest.mark.parametrize("n,T,H,hd", [(14336, 4096, 32, 128), (28672, 2048, 64, 128), (3072, 8192, 12, 64)])
+def test_syrk_other_baseline_shapes(ops, n, T, H, hd):
+    """Llama-3-8B (d_int 14336), Llama-2-70B (d_int 28672), OPT-125M (3072) operand widths."""
+    x = activations(T, n, n)
+    c = torch.zeros(n, n, device=DEV)
+    ops.syrk_(c, x)
+    xd = x.double()
+    for (r0, c0) in [(0, 0), (n - 200, n - 100), (n // 3, n // 2)]:
+        ref = xd[:, r0:r0 + 64].T @ xd[:, c0:c0 + 64]
+        got = c[r0:r0 + 64, c0:c0 + 64]
+        if r0 == c0:        # not finalised: only the upper triangle is defined
+            ref, got = torch.triu(ref), torch.triu(got)
+        assert rel(got, ref) < 1e-4
+    d = H * hd
+    ch = torch.zeros(H, hd, hd, device=DEV)
+    ops.syrk_heads_(ch, x[:, :d])
+    xh = xd[:, :d].view(T, H, hd)
+    for h in (0, H // 2, H - 1):
+        assert rel(ch[h], xh[:, h].T @ xh[:, h]) < 1e-4
+
+
+def test_type1_7b_scores_selection_and_solve(ops, c_mlp):
+    c, _ = c_mlp
+    n, d, ridge = c.shape[0], 4096, 1e-4
+    scores = ops.ridge_scores(c, ridge)
+    # scores are diag((C + ridge I)^-1): check against fp64 solves of (C + ridge I) x = e_j
+    a = c.double() + ridge * torch.eye(n, device=DEV, dtype=torch.float64)
+    chol = torch.linalg.cholesky(a)
+    js = torch.tensor([0, 17, 5503, 9999, n - 1], device=DEV)
+    e = torch.zeros(n, js.numel(), device=DEV, dtype=torch.float64)
+    e[js, torch.arange(js.numel())] = 1.0
+    xs = torch.cholesky_solve(e, chol)
+    want = xs[js, torch.arange(js.numel())]
+    assert rel(scores[js], want) < 1e-4
+    # selection: exactly k indices, strictly ascending, every kept score <= every dropped score
+    k = int(n * 0.75)
+    idx = ops.select_k(scores, k)
+    assert idx.numel() == k and bool((idx[1:] > idx[:-1]).all())
+    keep = torch.zeros(n, dtype=torch.bool, device=DEV)
+    keep[idx] = True
+    assert scores[keep].max() <= scores[~keep].min()
+    ref_idx = torch.sort(torch.topk(torch.linalg.inv(a).diagonal(), k, largest=False).indices).values
+    assert torch.equal(idx, ref_idx)
+    # Nystrom solve: residual of (C_kk + 1e-6 I) X = C_k: Wd^T in fp64
+    g = torch.Generator(device=DEV).manual_seed(3)
+    wd = (torch.randn(d, n, device=DEV, generator=g) * 0.02).bfloat16()
+    down = ops.nystrom_down(c, idx, wd)                   # [d, k] bf16
+    assert down.shape == (d, k)
+    cd = c.double()
+    ckk = cd[idx][:, idx] + 1e-6 * torch.eye(k, device=DEV, dtype=torch.float64)
+    rhs = cd[idx, :] @ wd.double().T
+    ref = torch.cholesky_solve(rhs, torch.linalg.cholesky(ckk)).T
+    assert rel(down, ref.bfloat16()) < 1e-3               # vs the reference's bf16-rounded result
+    assert (down == ref.bfloat16()).float().mean() > 0.97
+    up = ops.gather_rows(wd.T.contiguous(), idx)          # any [n, d] bf16 matrix
+    assert torch.equal(up, wd.T.contiguous()[idx])
+
+
+@pytest.mark.parametrize("H,KV", [(32, 32), (32, 8)])
+def test_type3_7b_shape_against_closed_form(ops, H, KV):
+    """d = 4096, hd = 128: per-head products O'V' against the fp64 closed form."""
+    d, hd, r, ridge = 4096, 128, 96, 1e-5
+    x = activations(8192, d, 11, spread=0.4)
+    c = torch.zeros(d, d, device=DEV)
+    ops.syrk_(c, x)
+    ops.finalize_sym_(c, 1.0 / 8192)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    wv = (torch.randn(KV * hd, d, device=DEV, generator=g) * 0.02).bfloat16()
+    wo = (torch.randn(d, H * hd, device=DEV, generator=g) * 0.02).bfloat16()
+    v, o = ops.vo_compress(c, ridge, wv, wo, H, KV, hd, r)
+    cr = c.double() + ridge * torch.eye(d, device=DEV, dtype=torch.float64)
+    grp = H // KV
+    for q in (0, H // 2 + 1, H - 1):
+        h = q // grp
+        wvh, woh = wv[h * hd:(h + 1) * hd].double(), wo[:, q * hd:(q + 1) * hd].double()
+        lam, vec = torch.linalg.eigh(wvh @ cr @ wvh.T)
+        lam, vec = lam.flip(0), vec.flip(1)
+        s = lam.clamp_min(0).sqrt()
+        if grp == 1:
+            b = (s[:, None] * (vec.T @ (woh.T @ woh) @ vec)) * s[None, :]
+            lp, up = torch.linalg.eigh(b)
+            up = up.flip(1)[:, :r]
+            v_ref = ((vec / s[None, :]) @ up).T @ wvh
+            o_ref = woh @ ((vec * s[None, :]) @ up)
+        else:
+            v_ref = (vec[:, :r] / s[None, :r]).T @ wvh
+            o_ref = woh @ (vec[:, :r] * s[None, :r])
+        prod = o[:, q * r:(q + 1) * r].double() @ v[h * r:(h + 1) * r].double()
+        assert rel(prod, o_ref @ v_ref) < 5e-3
+
+
+def test_type2_7b_shape(ops):
+    H, hd, r = 32, 128, 96
+    x = activations(4096, H * hd, 21)
+    cq = torch.zeros(H, hd, hd, device=DEV)
+    ck = torch.zeros(H, hd, hd, device=DEV)
+    ops.syrk_heads_(cq, x)
+    ops.syrk_heads_(ck, activations(4096, H * hd, 22))
+    mask = ops.qk_select(cq, ck, r, 0, 1e-4, 1e-4)
+    dq = torch.diagonal(cq, dim1=1, dim2=2).double() + 1e-4
+    dk = torch.diagonal(ck, dim1=1, dim2=2).double() + 1e-4
+    score = dq[:, :64] * dk[:, :64] + dq[:, 64:] * dk[:, 64:]
+    want = torch.topk(score, r // 2, dim=1).indices
+    assert torch.equal(mask[:, : r // 2], want) and torch.equal(mask[:, r // 2:], want + 64)
+    w = activations(H * hd, 4096, 23)
+    out = ops.gather_head_rows(w, mask, H, 1, hd)
+    rows = (torch.arange(H, device=DEV) * hd)[:, None] + mask
+    assert torch.equal(out, w[rows.reshape(-1)])
