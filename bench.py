@@ -40,13 +40,13 @@ HYPER = dict(compression_ratio=0.25, nystrom_ridge=1e-4, ridge_vo=1e-5, ridge_qk
 
 def ncu_traffic_bytes():
     """DRAM bytes (read + write) of one C_mlp SYRK launch from the committed ncu --set full capture."""
-    p = ROOT / "profiles" / "r1_syrk_ncu_full.json"
+    p = ROOT / "profiles" / "r1_syrk_pair_ncu_full.json"
     if not p.exists():
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     best = None
     for k in json.loads(p.read_text())["kernels"]:
-        if "<256>" not in k["kernel"]:
+        if "gemm_tn" not in k["kernel"]:
             continue
         tot = sum(float(k[m]["value"]) * mult[k[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         best = max(best or 0.0, tot)      # the n = 11008 launch is the largest <256> launch captured
@@ -335,7 +335,7 @@ def run_gpu_arm(args) -> None:
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * SEQ * 8,
                 "d2h_bytes_per_step": LAYERS * 8},
         "gpu_launches": args.steps * LAYERS * 5,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel<256> (C_mlp SYRK, n=11008, T=32768)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tn_pair_kernel, cta_group::2 256x256 tiles (C_mlp SYRK, n=11008, T=32768)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": ncu_traffic_bytes(),
                      "algorithmic_bytes": BATCH * SEQ * D_INT * 2 + D_INT * (D_INT + 1) * 4,

@@ -13,6 +13,7 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "mg_ptx.cuh"
@@ -59,9 +60,9 @@ struct Work {
   int mi, nj, kb0, kb1;
 };
 
-template <int BN>
+template <int BN, int BMT = BM>
 __device__ __forceinline__ Work decode_work(const KParams& p, int w) {
-  constexpr int R = BN / BM;
+  constexpr int R = BN / BMT;
   const int tile = w / p.ksplit;
   const int ks = w - tile * p.ksplit;
   Work o;
@@ -364,6 +365,196 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair engine: one 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2).
+//   * each CTA stages only ITS half of both operands (128 M-columns of A, 128 N-columns of B) —
+//     half the shared-memory fill and read traffic of the single-CTA tile per MMA flop;
+//   * both CTAs' TMA loads credit the LEADER's `full` barrier; the leader's elected thread issues
+//     tcgen05.mma.cta_group::2 (M = 256: rows 0-127 accumulate in the leader's TMEM, 128-255 in the
+//     peer's), and its commits are multicast to the `empty` / `tmem_full` barriers of both CTAs;
+//   * each CTA drains its own 128 TMEM lanes through the same TMA store / reduce-add epilogue and
+//     releases the accumulator by a remote arrive on the leader's `tmem_empty` barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairBM = 256, kPairBN = 256;
+constexpr int kPairStages = 6;
+constexpr uint32_t kPairStageBytes = 2 * kABytes;   // 16 KB of A + 16 KB of B per CTA
+constexpr uint32_t kPairEpiBytes = 4 * 2 * 4096;
+constexpr uint32_t kPairSmem = kPairStages * kPairStageBytes + kPairEpiBytes + 1024 + 512;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                        const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmD, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* epi_smem = smem + kPairStages * kPairStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + kPairEpiBytes);
+  uint64_t* empty = full + kPairStages;
+  uint64_t* tmem_full = empty + kPairStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * kEpiThreads);   // epilogue threads of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < p.total_work; w += n_clusters) {
+        const Work wk = decode_work<kPairBN, kPairBM>(p, w);
+        if (wk.kb0 >= wk.kb1) continue;
+        const int a_col = wk.mi * kPairBM + static_cast<int>(rank) * 128;
+        const int b_col = wk.nj * kPairBN + static_cast<int>(rank) * 128;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          for (int pr = 0; pr < p.npairs; ++pr) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            if (leader) mbar_expect_tx(&full[stage], 2 * kPairStageBytes);
+            const uint32_t full_leader = map_to_cta(smem_u32(&full[stage]), 0);
+            uint8_t* sa = smem + stage * kPairStageBytes;
+            uint8_t* sb = sa + kABytes;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              tma_load_3d_pair(sa + c * kBoxBytes, &tmA, full_leader, a_col + c * kChunkCols, kb * BK,
+                               p.pair_a[pr]);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              tma_load_3d_pair(sb + c * kBoxBytes, &tmB, full_leader, b_col + c * kChunkCols, kb * BK,
+                               p.pair_b[pr]);
+            if (++stage == kPairStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(kPairBM, kPairBN, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = cluster_id; w < p.total_work; w += n_clusters) {
+        const Work wk = decode_work<kPairBN, kPairBM>(p, w);
+        if (wk.kb0 >= wk.kb1) continue;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1u;
+        ++it;
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kPairBN);
+        uint32_t accum = 0;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          for (int pr = 0; pr < p.npairs; ++pr) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+            const uint32_t sb = sa + kABytes;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
+              umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accum);
+              accum = 1;
+            }
+            umma_commit_pair(&empty[stage]);
+            if (++stage == kPairStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit_pair(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int q = warp & 3;
+    uint8_t* wbuf = epi_smem + (warp - 2) * 8192;
+    int it = 0;
+    for (int w = cluster_id; w < p.total_work; w += n_clusters) {
+      const Work wk = decode_work<kPairBN, kPairBM>(p, w);
+      if (wk.kb0 >= wk.kb1) continue;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      ++it;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int64_t warp_row0 = static_cast<int64_t>(wk.mi) * kPairBM + rank * 128 + q * 32;
+      if (warp_row0 < p.M) {
+#pragma unroll 1
+        for (int cc = 0; cc < kPairBN / 32; ++cc) {
+          const int64_t gc0 = static_cast<int64_t>(wk.nj) * kPairBN + cc * 32;
+          if (gc0 >= p.N) break;
+          if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
+          float v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(as * kPairBN + cc * 32);
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
+          uint8_t* buf = wbuf + (cc & 1) * 4096;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2],
+                            p.alpha * v[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.epi == EPI_STORE) tma_store_2d(&tmD, buf, static_cast<int>(gc0), static_cast<int>(warp_row0));
+            else tma_reduce_add_2d(&tmD, buf, static_cast<int>(gc0), static_cast<int>(warp_row0));
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's smem / TMEM stay live until every MMA and remote arrive is done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -470,6 +661,15 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
 
   const bool bn256 = (a.tiles != TILES_DIAG) && a.N > 128;
   const int BN = bn256 ? 256 : 128;
+  // CTA-pair path: plain 2-D fp32 output reachable by the TMA epilogue and at least one full
+  // 256-row tile; MG_DISABLE_2CTA=1 forces the single-CTA kernel (A/B measurements).
+  static const bool pair_disabled = [] {
+    const char* e = std::getenv("MG_DISABLE_2CTA");
+    return e && e[0] == '1';
+  }();
+  const bool pair = !pair_disabled && a.tiles != TILES_DIAG && a.M >= 256 && a.N >= 256 &&
+                    ((reinterpret_cast<uintptr_t>(a.D) & 15) == 0) && (a.ldd % 4 == 0);
+  const int BMT = pair ? kPairBM : BM;
 
   KParams kp{};
   kp.M = a.M;
@@ -486,14 +686,14 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
     kp.pair_a[i] = a.pair_a[i];
     kp.pair_b[i] = a.pair_b[i];
   }
-  kp.MT = static_cast<int>((a.M + BM - 1) / BM);
+  kp.MT = static_cast<int>((a.M + BMT - 1) / BMT);
   kp.NT = static_cast<int>((a.N + BN - 1) / BN);
   if (a.tiles == TILES_FULL) {
     kp.ntiles = kp.MT * kp.NT;
   } else if (a.tiles == TILES_DIAG) {
     kp.ntiles = kp.MT;
   } else {
-    const int R = BN / BM;
+    const int R = BN / BMT;
     const int last = (R * kp.NT < kp.MT) ? R * kp.NT : kp.MT;
     kp.ntiles = R * (kp.NT - 1) * kp.NT / 2 + last;
   }
@@ -534,6 +734,20 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
     rc = diag128 ? make_out_map(&tmD, a.D, 128, a.M, 128) : make_out_map(&tmD, a.D, a.N, a.M, a.ldd);
     if (rc) return rc;
     kp.tma_epi = 1;
+  }
+  if (pair) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tn_pair_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+      if (e != cudaSuccess) return -1000 - static_cast<int>(e);
+      attr_set = true;
+    }
+    const int max_clusters = device_sm_count() / 2;
+    const int clusters = kp.total_work < max_clusters ? kp.total_work : max_clusters;
+    gemm_tn_pair_kernel<<<2 * clusters, kThreads, kPairSmem, stream>>>(tmA, tmB, tmD, kp);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
   }
   return bn256 ? launch_impl<256>(tmA, tmB, tmD, kp, stream)
                : launch_impl<128>(tmA, tmB, tmD, kp, stream);

@@ -162,7 +162,7 @@ int mg_syrk_bf16_f32(const void* X, int64_t T, int64_t n, int64_t ldx, float* C,
   a.tiles = mg::TILES_UPPER;
   a.epi = accumulate ? mg::EPI_ADD : mg::EPI_STORE;
   a.hd = 128;
-  a.ksplit = accumulate ? mg::segments_for(T) : 1;
+  a.ksplit = accumulate ? -mg::segments_for(T) : 1;   // auto split-K, at least the segment count
   return mg::gemm_tn_launch(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -25,6 +25,8 @@ OWN = ["bi_cosine_kernel", "finalize_sym_kernel", "scale_kernel", "split_planes_
 
 
 def short_name(name: str) -> str:
+    if "gemm_tn_pair_kernel" in name:
+        return "mg::gemm_tn_pair_kernel"
     if "gemm_tn_kernel" in name:
         return "mg::gemm_tn_kernel" + ("<256>" if "<256>" in name else "<128>")
     for own in OWN:
