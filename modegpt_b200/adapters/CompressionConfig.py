@@ -40,6 +40,7 @@ class CompressionConfig:
     eval_samples: int = 16         # held-out synthetic sequences for the perplexity check
     seed: int = 1234               # calibration token seed (reference seeds are 1234)
     keep_layers_in_memory: bool = False   # hand layers to convert_model without the disk round trip
+    stream_layers: bool = False           # layer-streamed calibration: one layer's statistics at a time
 
     _HELP: typing.ClassVar[dict] = {
         "order": "mlp,qk,vo  -- <method>,<method>,<method>",

@@ -18,7 +18,7 @@ import torch
 from . import distributed as D
 from .adapters.CompressionConfig import CompressionConfig
 from .adapters.model_adapter import ModelAdapter
-from .calibration import load_calibs
+from .calibration import block_influence, iter_layer_statistics, load_calibs
 from .compression.compress_mlp import compress_nystrom
 from .compression.compress_qk import compress_qk
 from .compression.compress_vo import compress_vo
@@ -84,7 +84,35 @@ def main(trial=None, config: CompressionConfig | None = None):
         timings[key] += time.perf_counter() - t0
         return out
 
-    for start in range(0, n_layers, LAYERS_PER_STEP):
+    if config.stream_layers:
+        # two passes over the (resident) hidden states: BI for every layer first — every rank's
+        # keep ratio depends on all of them — then one layer's statistics at a time, decomposed by
+        # the layer's owner and freed before the next layer is touched
+        bi_scores = timed("calibration_s", lambda: block_influence(adapter, dataset=config.dataset))
+        keep = allocate_global_sparsity(bi_scores, compression_ratio=config.compression_ratio,
+                                        smoothing=config.sparsity_smoothing,
+                                        max_sparsity=config.max_sparsity, adapter=adapter)
+        stats = iter_layer_statistics(adapter, dataset=config.dataset)
+        while True:
+            item = timed("calibration_s", lambda: next(stats, None))
+            if item is None:
+                break
+            l, c_mlp, c_q, c_k, c_x = item
+            one = lambda t: [t if i == l else None for i in range(n_layers)]
+            if "mlp" in config.order:
+                timed("mlp_s", lambda: compress_nystrom(adapter=adapter, cov=one(c_mlp), keep_ratios=keep,
+                                                        target_layers=[l]))
+            if "qk" in config.order:
+                masks = timed("qk_s", lambda: compress_qk(adapter=adapter, cov=(one(c_q), one(c_k)),
+                                                         keep_ratios=keep, target_layers=[l]))
+                rotary_masks.extend(masks or [])
+            if "vo" in config.order:
+                timed("vo_s", lambda: compress_vo(adapter=adapter, cov=one(c_x), keep_ratios=keep,
+                                                  target_layers=[l]))
+            del item, c_mlp, c_q, c_k, c_x
+        torch.cuda.empty_cache()
+
+    for start in (() if config.stream_layers else range(0, n_layers, LAYERS_PER_STEP)):
         target = list(range(start, min(n_layers, start + LAYERS_PER_STEP)))
         cov_mlp, cov_q, cov_k, cov_x, bi_scores = timed("calibration_s", lambda: load_calibs(
             adapter=adapter, n_samples=config.calib_size, batch_size=config.calibs_batch_size,

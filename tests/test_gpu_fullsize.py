@@ -161,3 +161,44 @@ def test_type2_7b_shape(ops):
     out = ops.gather_head_rows(w, mask, H, 1, hd)
     rows = (torch.arange(H, device=DEV) * hd)[:, None] + mask
     assert torch.equal(out, w[rows.reshape(-1)])
+
+
+def test_type1_70b_mlp_width(ops):
+    """Llama-2-70B MLP width (n = 28672, d = 8192, keep 0.7): scores, selection and the Nystrom
+    solve at the largest size BASELINE.json names, checked through fp64 solves / residuals."""
+    n, d, T, ridge = 28672, 8192, 32768, 1e-4
+    x = activations(T, n, 70, spread=0.2)
+    c = torch.zeros(n, n, device=DEV)
+    ops.syrk_(c, x)
+    ops.finalize_sym_(c, 1.0 / T)
+    del x
+    # T / n = 1.14: cond(C + ridge I) ~ 1e3-1e4.  The factorisation is fp32 (bf16x3 tensor-core
+    # products, fp64 diagonal blocks), so the score error scales like cond * 2^-24; with T < n the
+    # matrix is rank-deficient (cond ~ lambda_max / ridge ~ 1e7) and 1e-2 relative is the physics.
+    scores = ops.ridge_scores(c, ridge)
+    a = c.double()
+    a.diagonal().add_(ridge)
+    chol = torch.linalg.cholesky(a)
+    del a
+    js = torch.tensor([1, 9000, 20000, n - 2], device=DEV)
+    e = torch.zeros(n, js.numel(), device=DEV, dtype=torch.float64)
+    e[js, torch.arange(js.numel())] = 1.0
+    want = torch.cholesky_solve(e, chol)[js, torch.arange(js.numel())]
+    del chol, e
+    assert rel(scores[js], want) < 2e-3
+    k = int(n * 0.7)
+    idx = ops.select_k(scores, k)
+    keep = torch.zeros(n, dtype=torch.bool, device=DEV)
+    keep[idx] = True
+    assert idx.numel() == k and scores[keep].max() <= scores[~keep].min()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    wd = (torch.randn(d, n, device=DEV, generator=g) * 0.02).bfloat16()
+    down = ops.nystrom_down(c, idx, wd)                    # [d, k]
+    assert down.shape == (d, k) and bool(torch.isfinite(down.float()).all())
+    # residual of (C_kk + 1e-6 I) X = C_k: Wd^T on 64 right-hand sides, in fp64
+    cols = torch.arange(0, d, d // 64, device=DEV)[:64]
+    ckk = c[idx][:, idx].double()
+    ckk.diagonal().add_(1e-6)
+    rhs = c[idx, :].double() @ wd[cols].double().T         # [k, 64]
+    ref = torch.cholesky_solve(rhs, torch.linalg.cholesky(ckk))
+    assert rel(down[cols].T, ref.bfloat16()) < 5e-3

@@ -143,3 +143,50 @@ def test_cli_flow_on_synthetic_presets(tmp_path, preset, monkeypatch):
             assert (tmp_path / "layers" / f"layer_{i}_{suf}").exists()
     assert (tmp_path / "out" / "model" / "config.json").exists()
     assert (tmp_path / "metrics" / "metrics.json").exists()
+
+
+@pytest.mark.parametrize("preset", ["tiny-llama-gqa", "tiny-qwen3"])
+def test_layer_streamed_calibration_is_identical(preset):
+    """One layer's statistics at a time == all layers at once (same kernels, same order)."""
+    from modegpt_b200.adapters.CompressionConfig import CompressionConfig
+    from modegpt_b200.adapters.model_adapter import ModelAdapter
+    from modegpt_b200.calibration import block_influence, iter_layer_statistics, load_calibs
+    from modegpt_b200.eval import synthetic_tokens
+    from modegpt_b200.model_utils import build_synthetic_model
+
+    model = build_synthetic_model(preset, device=DEV, seed=1, max_positions=512)
+    adapter = ModelAdapter.from_model(model, None)
+    adapter.config = CompressionConfig(model=preset, dataset="synthetic", seq_len=192, calib_size=6,
+                                       calibs_batch_size=2)
+    tokens = synthetic_tokens(6, 192, model.config.vocab_size, 99).to(DEV)
+    adapter.calibs = [tokens[i:i + 2] for i in range(0, 6, 2)]
+    cov_mlp, cov_q, cov_k, cov_x, bi = load_calibs(adapter, 6, 2, dataset="synthetic")
+    bi_s = block_influence(adapter)
+    np.testing.assert_allclose(bi_s, bi, rtol=1e-9)
+    seen = []
+    for l, c_mlp, c_q, c_k, c_x in iter_layer_statistics(adapter):
+        seen.append(l)
+        assert rel(c_mlp.cpu().numpy(), cov_mlp[l].cpu().numpy()) < 1e-6
+        assert rel(c_x.cpu().numpy(), cov_x[l].cpu().numpy()) < 1e-6
+        assert rel(c_q.cpu().numpy(), cov_q[l].cpu().numpy()) < 1e-6
+        assert rel(c_k.cpu().numpy(), cov_k[l].cpu().numpy()) < 1e-6
+    assert seen == list(range(adapter.n_layers))
+
+
+def test_cli_flow_streamed(tmp_path, monkeypatch):
+    from modegpt_b200.adapters.CompressionConfig import CompressionConfig
+    from modegpt_b200.run_modegpt import main
+
+    monkeypatch.chdir(tmp_path)
+    cfg = CompressionConfig(
+        model="synthetic:tiny-llama-gqa", output_dir=str(tmp_path / "out"),
+        temp_storage_dir=str(tmp_path / "layers"), dataset="synthetic", order="mlp,qk,vo",
+        calib_size=4, calibs_batch_size=2, compression_ratio=0.25, max_sparsity=0.95,
+        sparsity_smoothing=0.04948, ridge_vo=1e-5, ridge_qk=1e-2, nystrom_ridge=1e-4, seq_len=128,
+        eval_samples=4, stream_layers=True)
+    ppl_streamed = main(config=cfg)
+    cfg2 = CompressionConfig(**{**cfg.to_dict(), "stream_layers": False,
+                                "output_dir": str(tmp_path / "out2"),
+                                "temp_storage_dir": str(tmp_path / "layers2")})
+    ppl_regular = main(config=cfg2)
+    assert np.isfinite(ppl_streamed) and abs(ppl_streamed - ppl_regular) < 1e-3 * ppl_regular
