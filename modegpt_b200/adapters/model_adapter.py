@@ -146,14 +146,17 @@ class ModelAdapter(ABC):
     def from_model(model: nn.Module, tokenizer=None) -> "ModelAdapter":
         from .LlamaAdapter import LlamaAdapter
         from .OPTAdapter import OPTAdapter
-        from .QwenAdapter import QwenAdapter
+        from .QwenAdapter import Qwen2Adapter, QwenAdapter
 
         inner = getattr(model, "model", None)
         if inner is not None and hasattr(inner, "decoder"):
             return OPTAdapter(model, tokenizer=tokenizer)
         if inner is not None and hasattr(inner, "layers"):
-            if "qwen3" in (getattr(model.config, "model_type", "") or ""):
+            model_type = getattr(model.config, "model_type", "") or ""
+            if "qwen3" in model_type:
                 return QwenAdapter(model, tokenizer=tokenizer)
+            if "qwen2" in model_type:
+                return Qwen2Adapter(model, tokenizer=tokenizer)
             return LlamaAdapter(model, tokenizer=tokenizer)
         raise RuntimeError("Unsupported model architecture")
 

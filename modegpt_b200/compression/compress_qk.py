@@ -71,7 +71,7 @@ def compress_layer(adapter: ModelAdapter, layer_idx: int, rank: int, cov_q_list:
     weights = {"q_proj": ops.gather_head_rows(wq, mask, H, H // KV, hd),
                "k_proj": ops.gather_head_rows(wk, mask, KV, 1, hd)}
     bq, bk = getattr(comps.query_proj, "bias", None), getattr(comps.key_proj, "bias", None)
-    if adapter.arch == "opt" and bq is not None:
+    if bq is not None and bk is not None:   # OPT, Qwen2: the bias entries follow their rows
         rows_q = (torch.arange(H, device=mask.device) * hd)[:, None] + mask.repeat_interleave(H // KV, 0)
         rows_k = (torch.arange(KV, device=mask.device) * hd)[:, None] + mask
         weights["q_bias"] = bq.detach()[rows_q.reshape(-1)]

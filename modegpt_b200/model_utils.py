@@ -22,16 +22,18 @@ PRESETS = {
     "llama-2-7b": ("llama", 4096, 32, 32, 128, 11008, 32, 32000),
     "llama-3-8b": ("llama", 4096, 32, 8, 128, 14336, 32, 128256),
     "qwen3-8b": ("qwen3", 4096, 32, 8, 128, 12288, 36, 151936),
+    "qwen2.5-7b": ("qwen2", 3584, 28, 4, 128, 18944, 28, 152064),
     "llama-2-70b": ("llama", 8192, 64, 8, 128, 28672, 80, 32000),
     "tiny-llama": ("llama", 256, 4, 4, 64, 512, 3, 512),
     "tiny-llama-gqa": ("llama", 256, 4, 2, 64, 512, 3, 512),
     "tiny-qwen3": ("qwen3", 256, 4, 2, 64, 512, 3, 512),
+    "tiny-qwen2": ("qwen2", 256, 4, 2, 64, 512, 3, 512),
     "tiny-opt": ("opt", 256, 4, 4, 64, 512, 3, 512),
 }
 
 
 def synthetic_config(preset: str, n_layers: int | None = None, max_positions: int = 2048):
-    from transformers import LlamaConfig, OPTConfig, Qwen3Config
+    from transformers import LlamaConfig, OPTConfig, Qwen2Config, Qwen3Config
 
     kind, d, H, KV, hd, d_int, L, vocab = PRESETS[preset]
     L = n_layers or L
@@ -39,6 +41,11 @@ def synthetic_config(preset: str, n_layers: int | None = None, max_positions: in
         return OPTConfig(hidden_size=d, num_attention_heads=H, ffn_dim=d_int, num_hidden_layers=L,
                          vocab_size=vocab, max_position_embeddings=max_positions,
                          word_embed_proj_dim=d, do_layer_norm_before=True)
+    if kind == "qwen2":     # Qwen2Config has no head_dim: hidden / heads
+        return Qwen2Config(hidden_size=d, num_attention_heads=H, num_key_value_heads=KV,
+                           intermediate_size=d_int, num_hidden_layers=L, vocab_size=vocab,
+                           max_position_embeddings=max_positions, tie_word_embeddings=False,
+                           use_sliding_window=False)
     cls = Qwen3Config if kind == "qwen3" else LlamaConfig
     return cls(hidden_size=d, num_attention_heads=H, num_key_value_heads=KV, head_dim=hd,
                intermediate_size=d_int, num_hidden_layers=L, vocab_size=vocab,

@@ -149,7 +149,7 @@ def test_adapter_tables_resolve_on_tiny_models():
     from modegpt_b200.model_utils import build_synthetic_model
 
     for preset, arch, has_gate in (("tiny-llama-gqa", "llama", True), ("tiny-qwen3", "qwen3", True),
-                                   ("tiny-opt", "opt", False)):
+                                   ("tiny-qwen2", "qwen2", True), ("tiny-opt", "opt", False)):
         model = build_synthetic_model(preset, device="cpu")
         a = ModelAdapter.from_model(model, tokenizer=None)
         assert a.arch == arch and a.n_layers == 3 and a.head_dim == 64 and a.d_model == 256
@@ -157,4 +157,4 @@ def test_adapter_tables_resolve_on_tiny_models():
         assert (mlp.gate_proj is not None) == has_gate and a.get_n_inner() == 512
         assert a.get_qk_tensors(0).query_proj.shape == (256, 256)
         assert a.get_vo_tensors(2).o_proj.shape[0] == 256
-        assert a.n_kv_heads == (2 if "gqa" in preset or preset == "tiny-qwen3" else 4)
+        assert a.n_kv_heads == (2 if "gqa" in preset or "qwen" in preset else 4)
