@@ -160,7 +160,8 @@ def workload_config(n_gpus: int) -> dict:
                         "(BASELINE configs[1]); random-init weights",
             "calibs_batch_size": BATCH, "seq_len": SEQ, "layers": LAYERS,
             "parallelism": f"token-sharded x{n_gpus}, one reduce-to-owner per layer at the end",
-            "l2_policy": "inputs larger than L2 (each statistics operand is 268-721 MB)", **HYPER}
+            "l2_policy": "inputs larger than L2 (each statistics operand is 268-721 MB)",
+            "forward": "HF modules, fused RMSNorm/SwiGLU/RoPE kernels (bit-compatible)", **HYPER}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -173,6 +174,7 @@ def run_gpu_arm(args) -> None:
     from modegpt_b200 import ops
     from modegpt_b200.adapters.CompressionConfig import CompressionConfig
     from modegpt_b200.adapters.model_adapter import ModelAdapter
+    from modegpt_b200.fused_forward import fused_elementwise
     from modegpt_b200.model_utils import build_synthetic_model
 
     rank = int(os.environ.get("RANK", "0"))
@@ -232,9 +234,14 @@ def run_gpu_arm(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    import contextlib
+
+    fuse = contextlib.nullcontext if args.eager_forward else (lambda: fused_elementwise(model))
+
     @torch.no_grad()
     def step(tokens):
-        body(tokens, use_cache=False)
+        with fuse():
+            body(tokens, use_cache=False)
 
     def reduce_all():
         for i in range(LAYERS):
@@ -339,7 +346,7 @@ def run_gpu_arm(args) -> None:
         "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * SEQ * 8,
                 "d2h_bytes_per_step": LAYERS * 8},
-        "gpu_launches": args.steps * LAYERS * 5,
+        "gpu_launches": args.steps * LAYERS * (5 if args.eager_forward else 10),
         "roofline": {"bound": "tensor", "kernel": "gemm_tn_pair_kernel, cta_group::2 256x256 tiles (C_mlp SYRK, n=11008, T=32768)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": ncu_traffic_bytes(),
@@ -361,6 +368,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--compress-layers", type=int, default=2)
+    ap.add_argument("--eager-forward", action="store_true",
+                    help="keep HF's eager elementwise kernels in the calibration forward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -117,6 +117,23 @@ int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, in
                    int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* ---- calibration forward: fused elementwise kernels ------------------------ */
+
+/* y[r, :] = weight * bf16(x32[r, :] * rsqrt(mean(x32[r, :]^2) + eps)), every intermediate rounded
+ * like HF's LlamaRMSNorm / Qwen2RMSNorm / Qwen3RMSNorm.forward (7 eager kernels -> 1). */
+int mg_rmsnorm_bf16(const void* x, int64_t ldx, int64_t rows, int64_t d, const void* weight, float eps,
+                    void* y, int64_t ldy, void* stream);
+
+/* out = bf16(silu(gate)) * up, elementwise over `count` bf16 values
+ * (LlamaMLP.forward: act_fn(gate_proj(x)) * up_proj(x); 2 eager kernels -> 1, bit-exact). */
+int mg_swiglu_bf16(const void* gate, const void* up, void* out, int64_t count, void* stream);
+
+/* out = bf16(x*cos) + bf16(rotate_half(x)*sin) on a contiguous [batch, seq, n_heads, head_dim]
+ * buffer; cos / sin are [*, seq, head_dim] with batch stride cos_batch_stride (0 = broadcast)
+ * (HF apply_rotary_pos_emb; 8 eager kernels per tensor -> 1, bit-exact). */
+int mg_rope_bf16(const void* x, void* out, const void* cos, const void* sin, int64_t batch,
+                 int64_t seq, int n_heads, int head_dim, int64_t cos_batch_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

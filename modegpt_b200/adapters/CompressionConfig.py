@@ -41,6 +41,7 @@ class CompressionConfig:
     seed: int = 1234               # calibration token seed (reference seeds are 1234)
     keep_layers_in_memory: bool = False   # hand layers to convert_model without the disk round trip
     stream_layers: bool = False           # layer-streamed calibration: one layer's statistics at a time
+    eager_forward: bool = False           # keep HF's eager elementwise kernels in the calibration forward
 
     _HELP: typing.ClassVar[dict] = {
         "order": "mlp,qk,vo  -- <method>,<method>,<method>",

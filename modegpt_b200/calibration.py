@@ -15,6 +15,7 @@ import torch
 from . import distributed as D
 from . import ops
 from .adapters.model_adapter import ModelAdapter
+from .fused_forward import fused_elementwise
 
 logger = logging.getLogger("MoDeGPT")
 
@@ -74,14 +75,18 @@ def _calibrate_model(adapter: ModelAdapter, n_samples: int, batch_size: int,
     # output closes the last Block-Influence pair, is part of it)
     body = getattr(model, "model", model)
     n_texts = 0
+    import contextlib
+
+    fuse = contextlib.nullcontext() if adapter.config.eager_forward else fused_elementwise(model)
     try:
-        for batch in D.shard_batches(adapter.calibs):
-            batch = batch.to(device, non_blocking=True)
-            n_texts += len(batch)
-            body(batch, use_cache=False)
-            # sum over the batch, mean over positions (src/calibration.py:122-124)
-            bi_total += bi_batch / batch.shape[1]
-            bi_batch.zero_()
+        with fuse:
+            for batch in D.shard_batches(adapter.calibs):
+                batch = batch.to(device, non_blocking=True)
+                n_texts += len(batch)
+                body(batch, use_cache=False)
+                # sum over the batch, mean over positions (src/calibration.py:122-124)
+                bi_total += bi_batch / batch.shape[1]
+                bi_batch.zero_()
     finally:
         for h in handles:
             h.remove()
@@ -119,6 +124,12 @@ def _calibrate_model(adapter: ModelAdapter, n_samples: int, batch_size: int,
 # to the layer's owner, handed to the caller (who decomposes and frees them) and the hidden states
 # advance.  Numerically identical to `load_calibs`: same kernels, same per-(layer, batch) order.
 # Pass 1 (`block_influence`) produces the BI scores every rank needs before any rank is known.
+
+
+def _forward_mode(adapter: ModelAdapter):
+    import contextlib
+
+    return contextlib.nullcontext() if adapter.config.eager_forward else fused_elementwise(adapter.model)
 
 
 class _LayerStepper:
@@ -173,13 +184,14 @@ def block_influence(adapter: ModelAdapter, dataset: str = "synthetic") -> list[f
     final_norm = _get(adapter.model, adapter.module_map.final_norm)
     total = torch.zeros(L, dtype=torch.float64, device=st.device)
     acc = torch.zeros(1, dtype=torch.float64, device=st.device)
-    for l in range(L):
-        for b in range(len(st.batches)):
-            out = st.run_layer(l, b)
-            acc.zero_()
-            ops.bi_cosine_(acc, st.hidden[b], final_norm(out) if l == L - 1 else out)
-            total[l] += acc[0] / out.shape[1]
-            st.hidden[b] = out
+    with _forward_mode(adapter):
+        for l in range(L):
+            for b in range(len(st.batches)):
+                out = st.run_layer(l, b)
+                acc.zero_()
+                ops.bi_cosine_(acc, st.hidden[b], final_norm(out) if l == L - 1 else out)
+                total[l] += acc[0] / out.shape[1]
+                st.hidden[b] = out
     count = torch.tensor([float(st.n_texts)], dtype=torch.float64, device=st.device)
     D.all_reduce_sum_(count)
     D.all_reduce_sum_(total)
@@ -215,8 +227,9 @@ def iter_layer_statistics(adapter: ModelAdapter, target_layers: list[int] | None
             adapter.register_hooks(l, st.blocks[l], cov_mlp_list=cov[0], cov_q_list=cov[1],
                                    cov_k_list=cov[2], cov_x_list=cov[3], handles=handles, logger=logger)
         try:
-            for b in range(len(st.batches)):
-                st.hidden[b] = st.run_layer(l, b)
+            with _forward_mode(adapter):
+                for b in range(len(st.batches)):
+                    st.hidden[b] = st.run_layer(l, b)
         finally:
             for h in handles:
                 h.remove()

@@ -218,3 +218,38 @@ def vo_compress(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tens
                              n_heads, n_kv_heads, hd, d, r, v_out.data_ptr(), v_out.stride(0),
                              o_out.data_ptr(), o_out.stride(0), ws.data_ptr(), nbytes, _stream()))
     return v_out, o_out
+
+
+# ------------------------------------------------------------------------------------------------
+# calibration forward: fused elementwise kernels
+# ------------------------------------------------------------------------------------------------
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    """HF *RMSNorm.forward in one kernel (bf16, last dim contiguous)."""
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    y = torch.empty(x2.shape, dtype=x.dtype, device=x.device)
+    check("mg_rmsnorm_bf16",
+          lib.mg_rmsnorm_bf16(x2.data_ptr(), x2.stride(0), x2.shape[0], x2.shape[1], weight.data_ptr(),
+                              eps, y.data_ptr(), y.stride(0), _stream()))
+    return y.view(shape)
+
+
+def swiglu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """bf16(silu(gate)) * up for contiguous bf16 tensors of equal shape."""
+    out = torch.empty_like(gate)
+    check("mg_swiglu_bf16",
+          lib.mg_swiglu_bf16(gate.data_ptr(), up.data_ptr(), out.data_ptr(), gate.numel(), _stream()))
+    return out
+
+
+def rope_bthd(x_bthd: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """Rotary embedding on a contiguous [B, T, H, hd] bf16 tensor; cos / sin [1 or B, T, hd]."""
+    B, T, H, hd = x_bthd.shape
+    out = torch.empty_like(x_bthd)
+    stride = 0 if cos.shape[0] == 1 else cos.stride(0)
+    check("mg_rope_bf16",
+          lib.mg_rope_bf16(x_bthd.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, T, H,
+                           hd, stride, _stream()))
+    return out
