@@ -40,7 +40,7 @@ HYPER = dict(compression_ratio=0.25, nystrom_ridge=1e-4, ridge_vo=1e-5, ridge_qk
 
 def ncu_traffic_bytes():
     """DRAM bytes (read + write) of one C_mlp SYRK launch from the committed ncu --set full capture."""
-    p = ROOT / "profiles" / "r1_syrk_pair_ncu_full.json"
+    p = ROOT / "profiles" / "r1_syrk_pair_banded_ncu_full.json"
     if not p.exists():
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -54,6 +54,7 @@ struct KParams {
   int vec_ok;  // D and ldd allow float4 accesses
   int klo_from_n;
   int tma_epi;  // epilogue through swizzled smem + TMA store / reduce-add
+  int band;     // TILES_UPPER with square tiles: rows per raster band (0 = column-major order)
 };
 
 struct Work {
@@ -72,6 +73,33 @@ __device__ __forceinline__ Work decode_work(const KParams& p, int w) {
   } else if (p.tiles == TILES_DIAG) {
     o.mi = tile;
     o.nj = tile;
+  } else if (R == 1 && p.band > 0) {
+    // Banded rasterisation of the upper triangle (square tiles): bands of `band` tile rows, each
+    // swept column by column with the row index fastest.  The ~74 tiles in flight at any moment
+    // then cover about band x (74/band) tiles and read band + 74/band distinct operand panels
+    // instead of ~NT + 2, which is what cuts the DRAM re-reads of X (every cluster walks K in step,
+    // so the shared panels hit in L2).
+    int t = tile, r0 = 0;
+    for (;;) {
+      const int g = min(p.band, p.MT - r0);
+      const int cnt = g * (p.NT - r0) - g * (g - 1) / 2;   // sum_{i<g} (NT - r0 - i)
+      if (t < cnt || r0 + g >= p.MT) break;
+      t -= cnt;
+      r0 += g;
+    }
+    const int g = min(p.band, p.MT - r0);
+    const int tri = g * (g + 1) / 2;
+    if (t < tri) {
+      int c = static_cast<int>((sqrtf(1.f + 8.f * static_cast<float>(t)) - 1.f) * 0.5f);
+      while (c > 0 && c * (c + 1) / 2 > t) --c;
+      while ((c + 1) * (c + 2) / 2 <= t) ++c;
+      o.nj = r0 + c;
+      o.mi = r0 + t - c * (c + 1) / 2;
+    } else {
+      const int u = t - tri;
+      o.nj = r0 + g + u / g;
+      o.mi = r0 + u % g;
+    }
   } else {
     // column nj of the tile grid owns rows mi in [0, min(R*(nj+1), MT)); only the last column can
     // be clipped, so prefix(nj) = R*nj*(nj+1)/2 for every valid nj.
@@ -613,7 +641,7 @@ int make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64
 
 template <int BN>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                const KParams& kp, cudaStream_t stream) {
+                const KParams& kp, int cta_cap, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -622,7 +650,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     if (e != cudaSuccess) return -1000 - static_cast<int>(e);
     attr_set = true;
   }
-  const int grid = kp.total_work < device_sm_count() ? kp.total_work : device_sm_count();
+  const int grid = kp.total_work < cta_cap ? kp.total_work : cta_cap;
   gemm_tn_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, tmD, kp);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
@@ -718,8 +746,18 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.atomic = kp.ksplit > 1;
   kp.klo_from_n = a.klo_from_n;
   kp.total_work = kp.ntiles * kp.ksplit;
+  if (pair && a.tiles == TILES_UPPER && kp.MT == kp.NT) {
+    static const int band_env = [] {
+      const char* e = std::getenv("MG_SYRK_BAND");
+      return e ? std::atoi(e) : 8;
+    }();
+    kp.band = band_env;
+  }
   kp.vec_ok = ((reinterpret_cast<uintptr_t>(a.D) & 15) == 0) &&
               (a.tiles == TILES_DIAG ? (kp.hd % 4 == 0) : (a.ldd % 4 == 0));
+
+  int cta_cap = device_sm_count();
+  if (a.max_ctas >= 2 && a.max_ctas < cta_cap) cta_cap = a.max_ctas;
 
   CUtensorMap tmA, tmB;
   int rc = make_plane_map(&tmA, a.A, a.M, a.K, a.lda, a.a_planes, a.a_plane_stride);
@@ -743,14 +781,14 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
       if (e != cudaSuccess) return -1000 - static_cast<int>(e);
       attr_set = true;
     }
-    const int max_clusters = device_sm_count() / 2;
+    const int max_clusters = cta_cap / 2;
     const int clusters = kp.total_work < max_clusters ? kp.total_work : max_clusters;
     gemm_tn_pair_kernel<<<2 * clusters, kThreads, kPairSmem, stream>>>(tmA, tmB, tmD, kp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
   }
-  return bn256 ? launch_impl<256>(tmA, tmB, tmD, kp, stream)
-               : launch_impl<128>(tmA, tmB, tmD, kp, stream);
+  return bn256 ? launch_impl<256>(tmA, tmB, tmD, kp, cta_cap, stream)
+               : launch_impl<128>(tmA, tmB, tmD, kp, cta_cap, stream);
 }
 
 }  // namespace mg

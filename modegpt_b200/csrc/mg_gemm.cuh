@@ -49,6 +49,9 @@ struct GemmArgs {
   // B is lower-triangular in (k, n): B[k, n] == 0 for n > k, so an N tile starting at column c0
   // only needs k >= c0 (used by the blocked triangular inverse).
   int klo_from_n;
+  // Upper bound on the CTAs of the persistent grid (0 = one per SM).  The blocked drivers keep a
+  // few SMs free so the latency-critical panel kernels of the look-ahead lane start at once.
+  int max_ctas;
 };
 
 // Returns 0, a negative argument error, or -1000 - cudaError_t.

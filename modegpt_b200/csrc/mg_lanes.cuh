@@ -1,0 +1,51 @@
+// mg_lanes.cuh — the three internal "lanes" (CUDA streams) a blocked factorisation is spread over.
+//
+// A right-looking blocked Cholesky is a chain of small, latency-bound panel kernels (potrf128 ->
+// trsm128) followed by a wide trailing update; run on one stream, the GPU idles behind the chain.
+// The drivers in mg_linalg.cu / mg_type1.cu therefore fork the caller's stream into
+//   chain : high priority — potrf128, trsm128 and the look-ahead update of the next block row;
+//   upd   : the rest of each trailing update (one panel behind the chain);
+//   tri   : work that only consumes finished block rows (triangular inverse rows, the Nystrom
+//           cross term and its forward substitution);
+// and join them back before returning, so to the caller every entry point is still an ordinary
+// stream-ordered call.  Streams and events are created once per device (no memory is allocated).
+// MG_SERIAL=1 collapses all lanes onto the caller's stream (A/B measurements, debugging).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mg {
+
+struct Lanes {
+  cudaStream_t chain = nullptr, upd = nullptr, tri = nullptr;
+  cudaStream_t user = nullptr;
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t trsm = nullptr;              // re-recorded by every panel: "block row pj is final"
+  cudaEvent_t upd_done[2] = {nullptr, nullptr};   // trailing update of panel pj (parity pj & 1)
+  cudaEvent_t misc[2] = {nullptr, nullptr};
+  bool serial = true;
+
+  void record(cudaEvent_t e, cudaStream_t on) const {
+    if (!serial) cudaEventRecord(e, on);
+  }
+  void wait(cudaStream_t who, cudaEvent_t e) const {
+    if (!serial) cudaStreamWaitEvent(who, e, 0);
+  }
+  int bulk_cta_cap() const;   // persistent-grid cap for GEMMs on upd / tri (0 = none)
+};
+
+// RAII: fork the caller's stream into the lanes (holding the per-device lane mutex), join on
+// destruction.  `ok()` is false if the streams could not be created; the drivers then run serial.
+class LaneScope {
+ public:
+  explicit LaneScope(cudaStream_t user);
+  ~LaneScope();
+  LaneScope(const LaneScope&) = delete;
+  LaneScope& operator=(const LaneScope&) = delete;
+  Lanes& lanes() { return lanes_; }
+
+ private:
+  Lanes lanes_;
+  void* lock_ = nullptr;
+};
+
+}  // namespace mg

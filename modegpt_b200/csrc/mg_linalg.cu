@@ -4,6 +4,9 @@
 //   * the right-looking blocked Cholesky driver whose TRSM and trailing SYRK run on tcgen05.
 #include "mg_linalg.cuh"
 
+#include <cstdlib>
+#include <mutex>
+
 #include "mg_gemm.cuh"
 #include "mg_prof.cuh"
 
@@ -515,42 +518,158 @@ void set_pairs6(GemmArgs& g) {
 }
 }  // namespace
 
-int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int* info,
-                   cudaStream_t s) {
+// ---------------------------------------------------------------------------------------------
+// lanes
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DeviceLanes {
+  std::mutex mu;
+  bool tried = false, ok = false;
+  Lanes proto;
+};
+
+DeviceLanes& device_lanes() {
+  static DeviceLanes per_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return per_dev[dev & 63];
+}
+
+bool lanes_disabled() {
+  static const bool off = [] {
+    const char* e = std::getenv("MG_SERIAL");
+    return e && e[0] == '1';
+  }();
+  return off;
+}
+}  // namespace
+
+int Lanes::bulk_cta_cap() const { return serial ? 0 : device_sm_count() - 4; }
+
+LaneScope::LaneScope(cudaStream_t user) {
+  lanes_.user = lanes_.chain = lanes_.upd = lanes_.tri = user;
+  lanes_.serial = true;
+  if (lanes_disabled()) return;
+  DeviceLanes& d = device_lanes();
+  d.mu.lock();
+  lock_ = &d;
+  if (!d.tried) {
+    d.tried = true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least urgent, hi = most urgent
+    bool ok = cudaStreamCreateWithPriority(&d.proto.chain, cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&d.proto.upd, cudaStreamNonBlocking, lo) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&d.proto.tri, cudaStreamNonBlocking, lo) == cudaSuccess;
+    cudaEvent_t* evs[] = {&d.proto.fork, &d.proto.join[0], &d.proto.join[1], &d.proto.join[2],
+                          &d.proto.trsm, &d.proto.upd_done[0], &d.proto.upd_done[1],
+                          &d.proto.misc[0], &d.proto.misc[1]};
+    for (cudaEvent_t* e : evs)
+      ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    d.ok = ok;
+  }
+  if (!d.ok) return;
+  lanes_ = d.proto;
+  lanes_.user = user;
+  lanes_.serial = false;
+  cudaEventRecord(lanes_.fork, user);
+  cudaStreamWaitEvent(lanes_.chain, lanes_.fork, 0);
+  cudaStreamWaitEvent(lanes_.upd, lanes_.fork, 0);
+  cudaStreamWaitEvent(lanes_.tri, lanes_.fork, 0);
+}
+
+LaneScope::~LaneScope() {
+  if (!lanes_.serial) {
+    cudaStream_t ls[3] = {lanes_.chain, lanes_.upd, lanes_.tri};
+    for (int i = 0; i < 3; ++i) {
+      cudaEventRecord(lanes_.join[i], ls[i]);
+      cudaStreamWaitEvent(lanes_.user, lanes_.join[i], 0);
+    }
+  }
+  if (lock_) static_cast<DeviceLanes*>(lock_)->mu.unlock();
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked Cholesky
+// ---------------------------------------------------------------------------------------------
+int CholStepper::step(int64_t pj) const {
+  const Lanes& L = *lanes;
   const int64_t np = ws.n_pad;
   const int64_t pstride = np * np;
+  const int64_t j0 = pj * kNB;
+  const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
+  float* tf = ws.t_fwd + pj * kTBlock;
+  float* tb = ws.t_bwd + pj * kTBlock;
   int rc;
-  for (int64_t j0 = 0, pj = 0; j0 < n; j0 += kNB, ++pj) {
-    const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
-    float* tf = ws.t_fwd + pj * kTBlock;
-    float* tb = ws.t_bwd + pj * kTBlock;
-    MG_TIMED(s, "chol.potrf128", rc = potrf128(A, ld, j0, nb, tf, tb, ws.u_planes, ws.l_planes, np, pstride, info, s));
-    if (rc) return rc;
-    const int64_t rest = n - j0 - nb;
-    if (rest <= 0) break;
-    // block row: U12 = U11^-T A12 (in place) + its bf16 planes (and those of U12^T)
-    float* a12 = A + j0 * ld + (j0 + nb);
-    __nv_bfloat16* u12 = ws.u_planes + j0 * np + (j0 + nb);
-    __nv_bfloat16* l21 = ws.l_planes ? ws.l_planes + (j0 + nb) * np + j0 : nullptr;
-    MG_TIMED(s, "chol.trsm128", rc = trsm128(tf, false, nb, a12, ld, rest, 1.f, a12, ld, u12, np, pstride,
-                                              l21, np, pstride, nullptr, s));
-    if (rc) return rc;
-    // trailing update on the upper triangle: A22 -= U12^T U12
-    GemmArgs t{};
+  MG_TIMED(L.chain, "chol.potrf128",
+           rc = potrf128(A, ld, j0, nb, tf, tb, ws.u_planes, ws.l_planes, np, pstride, info, L.chain));
+  if (rc) return rc;
+  const int64_t rest = n - j0 - nb;
+  if (rest <= 0) {
+    L.record(L.trsm, L.chain);
+    return 0;
+  }
+  // block row: U12 = U11^-T A12 (in place) + its bf16 planes (and those of U12^T)
+  float* a12 = A + j0 * ld + (j0 + nb);
+  __nv_bfloat16* u12 = ws.u_planes + j0 * np + (j0 + nb);
+  __nv_bfloat16* l21 = ws.l_planes ? ws.l_planes + (j0 + nb) * np + j0 : nullptr;
+  MG_TIMED(L.chain, "chol.trsm128",
+           rc = trsm128(tf, false, nb, a12, ld, rest, 1.f, a12, ld, u12, np, pstride, l21, np, pstride,
+                        nullptr, L.chain));
+  if (rc) return rc;
+  L.record(L.trsm, L.chain);
+
+  // trailing update A22 -= U12^T U12, split into the next block row (chain lane: it is all the
+  // next panel needs) and the rows below it (upd lane, hidden behind the next panel)
+  GemmArgs t{};
+  t.lda = t.ldb = np;
+  t.a_plane_stride = t.b_plane_stride = pstride;
+  t.a_planes = t.b_planes = kPlanes;
+  set_pairs6(t);
+  t.K = nb;
+  t.ldd = ld;
+  t.alpha = -1.f;
+  t.epi = EPI_ADD;
+  t.ksplit = 1;
+  if (L.serial) {
     t.A = t.B = u12;
-    t.lda = t.ldb = np;
-    t.a_plane_stride = t.b_plane_stride = pstride;
-    t.a_planes = t.b_planes = kPlanes;
-    set_pairs6(t);
     t.M = t.N = rest;
-    t.K = nb;
     t.D = A + (j0 + nb) * ld + (j0 + nb);
-    t.ldd = ld;
-    t.alpha = -1.f;
     t.tiles = TILES_UPPER;
-    t.epi = EPI_ADD;
-    t.ksplit = 1;
-    MG_TIMED(s, "chol.trailing_syrk", rc = gemm_tn_launch(t, s));
+    MG_TIMED(L.chain, "chol.trailing_syrk", rc = gemm_tn_launch(t, L.chain));
+    return rc;
+  }
+  const int64_t m1 = rest < kNB ? rest : kNB;
+  const int64_t rest2 = rest - m1;
+  if (rest2 > 0) {
+    GemmArgs r = t;
+    r.A = r.B = u12 + m1;
+    r.M = r.N = rest2;
+    r.D = A + (j0 + nb + m1) * ld + (j0 + nb + m1);
+    r.tiles = TILES_UPPER;
+    r.max_ctas = L.bulk_cta_cap();
+    L.wait(L.upd, L.trsm);
+    MG_TIMED(L.upd, "chol.trailing_syrk", rc = gemm_tn_launch(r, L.upd));
+    if (rc) return rc;
+    L.record(L.upd_done[pj & 1], L.upd);
+  }
+  // the update of panel pj-1 reaches block row pj+1 too: let it land first (ordered adds)
+  if (pj >= 1) L.wait(L.chain, L.upd_done[(pj - 1) & 1]);
+  t.A = u12;
+  t.B = u12;
+  t.M = m1;
+  t.N = rest;
+  t.D = A + (j0 + nb) * ld + (j0 + nb);
+  t.tiles = TILES_FULL;   // 128 x rest: the strict lower part of its diagonal block is scratch
+  MG_TIMED(L.chain, "chol.row_update", rc = gemm_tn_launch(t, L.chain));
+  return rc;
+}
+
+int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int* info,
+                   const Lanes& lanes) {
+  CholStepper st{A, n, ld, ws, info, &lanes};
+  for (int64_t pj = 0; pj < st.panels(); ++pj) {
+    const int rc = st.step(pj);
     if (rc) return rc;
   }
   return 0;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mg_lanes.cuh"
+
 namespace mg {
 
 constexpr int kNB = 128;      // panel width of every blocked algorithm
@@ -55,8 +57,25 @@ struct CholWorkspace {
   int64_t n_pad;
 };
 
-// A (fp32, n x n, upper triangle) -> U with U^T U = A, in place; fills ws.
+// A (fp32, n x n, upper triangle) -> U with U^T U = A, in place; fills ws.  Right-looking, panel
+// 128, with one panel of look-ahead over the lanes (mg_lanes.cuh).  `step(pj)` enqueues panel pj:
+//   chain : potrf128(pj), trsm128(pj) [records lanes.trsm], then the update of block row pj+1
+//           (after the upd lane has finished panel pj-1, which keeps the L2 reduce-adds ordered
+//           and the result deterministic);
+//   upd   : waits for lanes.trsm, updates the rows below block row pj+1, records upd_done[pj&1].
+// Callers interleave their own per-panel work on the tri lane between steps (it may wait on
+// lanes.trsm right after step(pj) to consume block row pj).
+struct CholStepper {
+  float* A;
+  int64_t n, ld;
+  CholWorkspace ws;
+  int* info;
+  const Lanes* lanes;
+  int64_t panels() const { return (n + kNB - 1) / kNB; }
+  int step(int64_t pj) const;
+};
+
 int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int* info,
-                   cudaStream_t s);
+                   const Lanes& lanes);
 
 }  // namespace mg

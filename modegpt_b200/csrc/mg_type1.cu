@@ -315,31 +315,38 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
   const int64_t np = w.chol.n_pad;
   int rc;
 
+  mg::LaneScope scope(s);
+  const mg::Lanes& L = scope.lanes();
+
   copy_ridge_kernel<<<dim3(static_cast<unsigned>((n + 1023) / 1024 < 8 ? (n + 1023) / 1024 : 8),
                            static_cast<unsigned>(n)),
-                      256, 0, s>>>(C, ldc, w.a, np, n, ridge);
+                      256, 0, L.chain>>>(C, ldc, w.a, np, n, ridge);
   if ((rc = cuda_rc())) return rc;
-  rc = mg::cholesky_upper(w.a, n, np, w.chol, info, s);
-  if (rc) return rc;
 
   // ---- blocked inverse of U, stored transposed (Y = U^-T, lower) as bf16 planes; the scores are
-  //      the column sums of squares of Y.
-  cudaMemsetAsync(w.y_planes, 0, sizeof(bf16) * kPlanes * np * np, s);
-  cudaMemsetAsync(scores, 0, sizeof(float) * n, s);
+  //      the column sums of squares of Y.  Row block pj of Y only needs block rows 0..pj of U, so
+  //      it is enqueued on the tri lane right behind Cholesky panel pj and runs concurrently with
+  //      the factorisation of the later panels.
+  cudaMemsetAsync(w.y_planes, 0, sizeof(bf16) * kPlanes * np * np, L.tri);
+  cudaMemsetAsync(scores, 0, sizeof(float) * n, L.tri);
   const int64_t pstride = np * np;
-  identity_kernel<<<(kNB * kNB + 255) / 256, 256, 0, s>>>(w.ident, kNB);
+  identity_kernel<<<(kNB * kNB + 255) / 256, 256, 0, L.tri>>>(w.ident, kNB);
   if ((rc = cuda_rc())) return rc;
+
+  mg::CholStepper chol{w.a, n, np, w.chol, info, &L};
   for (int64_t j0 = 0, pj = 0; j0 < n; j0 += kNB, ++pj) {
+    if ((rc = chol.step(pj))) return rc;
+    L.wait(L.tri, L.trsm);
     const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
     const float* tf = w.chol.t_fwd + pj * mg::kTBlock;
     // diagonal block Y[jb, jb] = U_jj^-T (solve U_jj^T X = I)
-    MG_TIMED(s, "trtri.diag_trsm", rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
-                                                    w.y_planes + j0 * np + j0, np, pstride, nullptr, 0, 0,
-                                                    scores + j0, s));
+    MG_TIMED(L.tri, "trtri.diag_trsm", rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
+                                                        w.y_planes + j0 * np + j0, np, pstride, nullptr, 0, 0,
+                                                        scores + j0, L.tri));
     if (rc) return rc;
     if (j0 == 0) continue;
     // Tt[nb, j0] = U[0:j0, jb]^T * Y[0:j0, 0:j0]
-    cudaMemsetAsync(w.tt, 0, sizeof(float) * kNB * np, s);
+    cudaMemsetAsync(w.tt, 0, sizeof(float) * kNB * np, L.tri);
     mg::GemmArgs g{};
     g.A = w.chol.u_planes + j0;
     g.lda = np;
@@ -360,12 +367,13 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
     g.epi = mg::EPI_ADD;
     g.ksplit = 0;
     g.klo_from_n = 1;
-    MG_TIMED(s, "trtri.gemm1", rc = mg::gemm_tn_launch(g, s));
+    g.max_ctas = L.bulk_cta_cap();
+    MG_TIMED(L.tri, "trtri.gemm1", rc = mg::gemm_tn_launch(g, L.tri));
     if (rc) return rc;
     // Y[jb, 0:j0] = -U_jj^-T Tt : planes + column sums of squares in one pass
-    MG_TIMED(s, "trtri.row_trsm", rc = mg::trsm128(tf, false, nb, w.tt, np, j0, -1.f, nullptr, 0,
-                                                   w.y_planes + j0 * np, np, pstride, nullptr, 0, 0,
-                                                   scores, s));
+    MG_TIMED(L.tri, "trtri.row_trsm", rc = mg::trsm128(tf, false, nb, w.tt, np, j0, -1.f, nullptr, 0,
+                                                       w.y_planes + j0 * np, np, pstride, nullptr, 0, 0,
+                                                       scores, L.tri));
     if (rc) return rc;
   }
   mg::Prof::get().report(s, "mg_ridge_scores_f32");
@@ -427,14 +435,18 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   const int64_t kp = w.chol.n_pad, dp = mg::round_up(d, 64);
   int rc;
 
-  // operands of the cross term  rhs[k, d] = C[idx, :] W_down^T = (C[:, idx])^T (W_down^T)
+  mg::LaneScope scope(s);
+  const mg::Lanes& L = scope.lanes();
+
+  // tri lane: operands of the cross term  rhs[k, d] = C[idx, :] W_down^T = (C[:, idx])^T (W_down^T)
+  // — independent of the factorisation of C_kk, which starts at once on the chain lane
   gather_cols_planes_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
                                    static_cast<unsigned>(n)),
-                              256, 0, s>>>(C, ldc, n, idx, k, w.g_planes, kp, n * kp);
+                              256, 0, L.tri>>>(C, ldc, n, idx, k, w.g_planes, kp, n * kp);
   if ((rc = cuda_rc())) return rc;
   transpose_to_bf16_kernel<bf16><<<dim3(static_cast<unsigned>((n + 31) / 32),
                                         static_cast<unsigned>((d + 31) / 32)),
-                                   256, 0, s>>>(static_cast<const bf16*>(Wd), ldwd, d, n, w.wdt, dp);
+                                   256, 0, L.tri>>>(static_cast<const bf16*>(Wd), ldwd, d, n, w.wdt, dp);
   if ((rc = cuda_rc())) return rc;
   {
     mg::GemmArgs g{};
@@ -459,27 +471,34 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
     g.tiles = mg::TILES_FULL;
     g.epi = mg::EPI_STORE;
     g.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    g.max_ctas = L.bulk_cta_cap();
+    MG_TIMED(L.tri, "nystrom.cross_term", rc = mg::gemm_tn_launch(g, L.tri));
+    if (rc) return rc;
   }
-  // C_kk + jitter I and its Cholesky factor (planes of U and of L = U^T)
+  // chain lane: C_kk + jitter I and its Cholesky factor (planes of U and of L = U^T)
   gather_sym_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
                            static_cast<unsigned>(k)),
-                      256, 0, s>>>(C, ldc, idx, k, w.ckk, kp, jitter);
+                      256, 0, L.chain>>>(C, ldc, idx, k, w.ckk, kp, jitter);
   if ((rc = cuda_rc())) return rc;
-  if ((rc = mg::cholesky_upper(w.ckk, k, kp, w.chol, info, s))) return rc;
 
   const int64_t pstride = kp * kp;
   const int64_t panels = (k + kNB - 1) / kNB;
-  // ---- forward solve  U^T Z = rhs  (right-looking, in place)
+  mg::CholStepper chol{w.ckk, k, kp, w.chol, info, &L};
+  // ---- forward solve  U^T Z = rhs  (right-looking, in place) rides one panel behind the
+  //      factorisation on the tri lane: step pi needs block row pi of U and nothing later
   for (int64_t pi = 0; pi < panels; ++pi) {
+    if ((rc = chol.step(pi))) return rc;
+    L.wait(L.tri, L.trsm);
     const int64_t i0 = pi * kNB;
     const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
     float* bi = w.rhs + i0 * dp;
     const int64_t rest = k - i0 - nb;
     // Z_i = U_ii^-T B_i (+ planes of Z_i for the update below)
-    if ((rc = mg::trsm128(w.chol.t_fwd + pi * mg::kTBlock, false, nb, bi, dp, d, 1.f, bi, dp,
-                          rest > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr, s)))
-      return rc;
+    MG_TIMED(L.tri, "nystrom.fwd_trsm",
+             rc = mg::trsm128(w.chol.t_fwd + pi * mg::kTBlock, false, nb, bi, dp, d, 1.f, bi, dp,
+                              rest > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
+                              L.tri));
+    if (rc) return rc;
     if (rest <= 0) break;
     mg::GemmArgs t{};
     t.A = w.chol.u_planes + i0 * kp + (i0 + nb);  // B[rest] -= U[ib, rest]^T Z_i
@@ -500,16 +519,25 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
     t.tiles = mg::TILES_FULL;
     t.epi = mg::EPI_ADD;
     t.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(t, s))) return rc;
+    t.max_ctas = L.bulk_cta_cap();
+    MG_TIMED(L.tri, "nystrom.fwd_update", rc = mg::gemm_tn_launch(t, L.tri));
+    if (rc) return rc;
   }
-  // ---- backward solve  U X = Z
+  // ---- backward solve  U X = Z  on the chain lane, once the forward pass and every trailing
+  //      update have landed
+  L.record(L.misc[0], L.tri);
+  L.wait(L.chain, L.misc[0]);
+  L.record(L.misc[1], L.upd);
+  L.wait(L.chain, L.misc[1]);
   for (int64_t pi = panels - 1; pi >= 0; --pi) {
     const int64_t i0 = pi * kNB;
     const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
     float* zi = w.rhs + i0 * dp;
-    if ((rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
-                          i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr, s)))
-      return rc;
+    MG_TIMED(L.chain, "nystrom.bwd_trsm",
+             rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
+                              i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
+                              L.chain));
+    if (rc) return rc;
     if (i0 == 0) break;
     mg::GemmArgs t{};
     t.A = w.chol.l_planes + i0 * kp;  // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
@@ -530,13 +558,16 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
     t.tiles = mg::TILES_FULL;
     t.epi = mg::EPI_ADD;
     t.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(t, s))) return rc;
+    MG_TIMED(L.chain, "nystrom.bwd_update", rc = mg::gemm_tn_launch(t, L.chain));
+    if (rc) return rc;
   }
   // ---- W_down' [d, k] = X^T, bf16
   transpose_to_bf16_kernel<float><<<dim3(static_cast<unsigned>((d + 31) / 32),
                                          static_cast<unsigned>((k + 31) / 32)),
-                                    256, 0, s>>>(w.rhs, dp, k, d, static_cast<bf16*>(Wd_out), ld_out);
-  return cuda_rc();
+                                    256, 0, L.chain>>>(w.rhs, dp, k, d, static_cast<bf16*>(Wd_out), ld_out);
+  rc = cuda_rc();
+  mg::Prof::get().report(s, "mg_nystrom_down_f32");
+  return rc;
 }
 
 }  // extern "C"
