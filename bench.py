@@ -333,6 +333,30 @@ def run_gpu_arm(args) -> None:
                         "ms_per_layer": stage_ms, "layers_timed": len(layers),
                         "note": "type I (n=11008, r=8256) + II + III (MHA, 32 heads) per layer, "
                                 "in-memory hand-off"}
+            # the same stages writing the reference's layer_{i}_{mlp,qk,vo} files through the
+            # asynchronous writer, final flush included (a full run hides the writes of all but
+            # the last layers behind the next layers' kernels; with so few layers it cannot)
+            import shutil
+            import tempfile
+
+            tmp = tempfile.mkdtemp(prefix="mg_layers_")
+            adapter.config.keep_layers_in_memory = False
+            adapter.config.temp_storage_dir = tmp
+            try:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                compress_nystrom(adapter, cov_mlp, keep, layers)
+                compress_qk(adapter, (cov_q, cov_k), keep, target_layers=layers)
+                compress_vo(adapter, cov_x, keep, target_layers=layers)
+                adapter.flush_saves()
+                torch.cuda.synchronize()
+                compress["s_per_layer_with_files"] = (time.perf_counter() - t0) / len(layers)
+                compress["file_bytes_per_layer"] = sum(
+                    os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp)) / len(layers)
+            finally:
+                adapter.config.keep_layers_in_memory = True
+                adapter._layer_cache.clear()
+                shutil.rmtree(tmp, ignore_errors=True)
 
     if rank != 0:
         if world > 1:

@@ -135,6 +135,8 @@ class ModelAdapter(ABC):
         self.calibs = None            # pre-seeded list of [B, T] int64 batches (synthetic seam)
         self.bi_scores = None
         self._layer_store: dict[tuple[int, str], dict[str, Tensor]] = {}
+        self._layer_cache: dict[tuple[int, str], dict[str, Tensor]] = {}   # device copies of written layers
+        self._writer = None           # handoff.LayerWriter, created on the first asynchronous save
         self.metrics = {
             "RunName": datetime.now().strftime("%Y_%m_%d--%H_%M_%S"),
             "RunDate": datetime.now().strftime("%b %d, %Y %I:%M %p"),
@@ -350,16 +352,42 @@ class ModelAdapter(ABC):
 
     # ---- stage hand-off (model_adapter.py:184-237) --------------------------------------------
     def save_layer(self, output_dir: str, suffix: str, weights: dict[str, Tensor], layer_idx) -> None:
+        """`layer_{i}_{suffix}` hand-off (model_adapter.py:184-191).  Same file, same dict; by default
+        it is written by the asynchronous `handoff.LayerWriter` (files are complete after
+        `flush_saves()`), and while device memory is plentiful the tensors also stay resident so
+        `convert_model` on this rank does not read them back.  `--sync_save` restores the reference's
+        blocking `torch.save`; `--keep_layers_in_memory` skips the files altogether."""
         if self.config.keep_layers_in_memory:
             self._layer_store[(int(layer_idx), suffix)] = weights
             return
         output_dir = os.path.expandvars(output_dir)
-        os.makedirs(output_dir, exist_ok=True)
-        torch.save(weights, os.path.join(output_dir, f"layer_{layer_idx}_{suffix}"))
+        path = os.path.join(output_dir, f"layer_{layer_idx}_{suffix}")
+        if self.config.sync_save:
+            os.makedirs(output_dir, exist_ok=True)
+            torch.save(weights, path)
+            return
+        if self._writer is None:
+            from ..handoff import LayerWriter
+
+            self._writer = LayerWriter()
+        self._writer.submit(path, weights)
+        first = next(iter(weights.values()))
+        if first.is_cuda:
+            free, total = torch.cuda.mem_get_info(first.device)
+            if free > 0.3 * total:
+                self._layer_cache[(int(layer_idx), suffix)] = weights
+
+    def flush_saves(self) -> None:
+        """Block until every submitted layer file is on disk (raises if a write failed)."""
+        if self._writer is not None:
+            self._writer.flush()
 
     def load_layer(self, saved_layers_dir: str, suffix: str, layer_idx: int, device) -> dict:
         if (layer_idx, suffix) in self._layer_store:
             return self._layer_store[(layer_idx, suffix)]
+        if (layer_idx, suffix) in self._layer_cache:
+            return self._layer_cache.pop((layer_idx, suffix))
+        self.flush_saves()
         path = os.path.join(os.path.expandvars(saved_layers_dir), f"layer_{layer_idx}_{suffix}")
         return torch.load(path, map_location=device)
 
@@ -369,11 +397,13 @@ class ModelAdapter(ABC):
         device = next(self.model.parameters()).device
 
         def linear(weight: Tensor, bias: Tensor | None = None) -> nn.Linear:
-            lin = nn.Linear(weight.shape[1], weight.shape[0], bias=bias is not None, device=device,
+            # built on the meta device and given its storage directly: no random init, no extra copy
+            # when the hand-off tensor is already a contiguous bf16 tensor on the device
+            lin = nn.Linear(weight.shape[1], weight.shape[0], bias=bias is not None, device="meta",
                             dtype=torch.bfloat16)
-            lin.weight.data.copy_(weight)
+            lin.weight = nn.Parameter(weight.detach().to(device=device, dtype=torch.bfloat16).contiguous())
             if bias is not None:
-                lin.bias.data.copy_(bias)
+                lin.bias = nn.Parameter(bias.detach().to(device=device, dtype=torch.bfloat16).contiguous())
             return lin
 
         for suffix in suffixes:

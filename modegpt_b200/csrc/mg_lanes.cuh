@@ -1,4 +1,4 @@
-// mg_lanes.cuh — the three internal "lanes" (CUDA streams) a blocked factorisation is spread over.
+// mg_lanes.cuh — the internal "lanes" (CUDA streams) a blocked factorisation is spread over.
 //
 // A right-looking blocked Cholesky is a chain of small, latency-bound panel kernels (potrf128 ->
 // trsm128) followed by a wide trailing update; run on one stream, the GPU idles behind the chain.
@@ -7,6 +7,8 @@
 //   upd   : the rest of each trailing update (one panel behind the chain);
 //   tri   : work that only consumes finished block rows (triangular inverse rows, the Nystrom
 //           cross term and its forward substitution);
+//   tri2  : the part of a triangular-inverse row that does not depend on the previous row
+//           (look-ahead for the tri lane's own chain);
 // and join them back before returning, so to the caller every entry point is still an ordinary
 // stream-ordered call.  Streams and events are created once per device (no memory is allocated).
 // MG_SERIAL=1 collapses all lanes onto the caller's stream (A/B measurements, debugging).
@@ -16,11 +18,14 @@
 namespace mg {
 
 struct Lanes {
-  cudaStream_t chain = nullptr, upd = nullptr, tri = nullptr;
+  cudaStream_t chain = nullptr, upd = nullptr, tri = nullptr, tri2 = nullptr;
   cudaStream_t user = nullptr;
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t trsm = nullptr;              // re-recorded by every panel: "block row pj is final"
   cudaEvent_t upd_done[2] = {nullptr, nullptr};   // trailing update of panel pj (parity pj & 1)
+  cudaEvent_t diag_done[2] = {nullptr, nullptr};  // triangular-inverse diagonal block of panel pj
+  cudaEvent_t row_done[2] = {nullptr, nullptr};   // triangular-inverse block row pj is final
+  cudaEvent_t bulk_done[2] = {nullptr, nullptr};  // look-ahead part of the row's cross product
   cudaEvent_t misc[2] = {nullptr, nullptr};
   bool serial = true;
 

@@ -9,6 +9,7 @@
 
 #include "mg_gemm.cuh"
 #include "mg_prof.cuh"
+#include "mg_ptx.cuh"
 
 namespace mg {
 
@@ -29,6 +30,18 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16
   mid = __float2bfloat16_rn(r1);
   const float r2 = r1 - __bfloat162float(mid);  // exact
   lo = __float2bfloat16_rn(r2);
+}
+
+// 1/sqrt(x) for x in the float range: single-precision seed + two Newton steps (full double
+// accuracy, a third of the latency of the library routine; the pivot loops sit on it).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y = static_cast<double>(rsqrtf(static_cast<float>(x)));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -100,16 +113,14 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int kDiagLd = kNB + 2;   // even: rows stay 16-byte aligned for double2 accesses
 constexpr int kPotrfThreads = 512;
-constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 64);
+constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 128);
 
 __global__ void __launch_bounds__(kPotrfThreads, 1)
     potrf128_kernel(float* __restrict__ A, int64_t ld, int64_t j0, int nb,
-                    float* __restrict__ t_fwd, float* __restrict__ t_bwd,
-                    __nv_bfloat16* __restrict__ u_planes, __nv_bfloat16* __restrict__ l_planes,
-                    int64_t ld_up, int64_t up_plane_stride, int* __restrict__ info) {
+                    float* __restrict__ t_fwd, float* __restrict__ t_bwd, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
   double* a = sm;                     // [128][130], upper triangle live
-  double* invd = sm + kNB * kDiagLd;  // [32] reciprocal pivots of the current sub-panel, + [32] pivot row
+  double* invd = sm + kNB * kDiagLd;  // [32] reciprocal pivots of the current sub-panel, + [2][32] pivot row
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
 
@@ -126,40 +137,54 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
   const int nsub = (nb + 31) / 32;
   for (int kb = 0; kb < nsub; ++kb) {
     const int c0 = kb * 32;
-    // (1) 32 x 32 diagonal block, one warp: lane i owns ROW i in registers; each step the scaled
-    //     pivot row goes through shared memory (broadcast reads) instead of 31 double shuffles
+    // (1) 32 x 32 diagonal block, one warp, lane k owns COLUMN k in registers (rows 0..k).
+    //     Step j: lane j's reciprocal pivot is broadcast by shuffle, every lane scales its own
+    //     entry of pivot row j (u_jk), folds it into its own diagonal and starts the rsqrt of that
+    //     diagonal at once — lane j+1's is the next pivot, so the long-latency rsqrt overlaps the
+    //     off-diagonal updates below — then the pivot row is exchanged through a double-buffered
+    //     32-entry shared array (one parallel store, broadcast loads).
     if (warp == 0) {
-      double* urow = invd + 32;          // [32] scaled pivot row
-      double row[32];
+      double* urow = invd + 32;          // [2][32] pivot row exchange (16-byte aligned)
+      double col[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) row[k] = (k >= lane) ? a[(c0 + lane) * kDiagLd + c0 + k] : 0.0;
+      for (int i = 0; i < 32; ++i) col[i] = a[(c0 + i) * kDiagLd + c0 + lane];   // rows > lane: don't-care
+      double diag = col[0];
+#pragma unroll
+      for (int i = 1; i < 32; ++i) diag = (i == lane) ? col[i] : diag;
+      double inv_own = rsqrt_pos(diag);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (lane == j) {
-          double piv = row[j];
-          if (!(piv > 0.0)) {
+        if (lane == j && !(diag >= 1e-30 && diag <= 1e30)) {   // rare: non-positive (reported) / out of float range
+          if (!(diag > 0.0)) {
             if (c0 + j < nb) atomicCAS(info, 0, static_cast<int>(j0 + c0 + j + 1));
-            piv = 1e-30;
+            diag = 1e-30;
           }
-          const double inv = rsqrt(piv);
-          invd[j] = inv;
-          row[j] = piv * inv;
-#pragma unroll
-          for (int k = j + 1; k < 32; ++k) row[k] *= inv;
-#pragma unroll
-          for (int k = j; k < 32; ++k) urow[k] = row[k];
+          inv_own = rsqrt(diag);
         }
+        const double inv = __shfl_sync(0xffffffffu, inv_own, j);
+        // u_jk: own entry of pivot row j (lane j: the diagonal sqrt(d_j); lanes < j: unused)
+        const double u = (lane == j ? diag : col[j]) * inv;
+        diag = (lane > j) ? fma(-u, u, diag) : diag;
+        if (lane == j) invd[j] = inv;
+        double* ur = urow + (j & 1) * 32;
+        ur[lane] = u;
         __syncwarp();
-        if (lane > j) {
-          const double mult = urow[lane];
+        // lane j+1's value is the next pivot's: issued here so that its dependent chain interleaves
+        // with the (independent) row updates below
+        inv_own = rsqrt_pos(diag);
+        // rows j+1 .. 31 of the own column; entries at or below the own diagonal are don't-care,
+        // so the pivot row is loaded and applied without predicates (batched 16-byte loads)
 #pragma unroll
-          for (int k = j + 1; k < 32; ++k) row[k] = fma(-mult, urow[k], row[k]);
+        for (int i2 = (j + 1) / 2; i2 < 16; ++i2) {
+          const double2 pr = *reinterpret_cast<const double2*>(ur + 2 * i2);
+          if (2 * i2 > j) col[2 * i2] = fma(-pr.x, u, col[2 * i2]);
+          col[2 * i2 + 1] = fma(-pr.y, u, col[2 * i2 + 1]);
         }
-        __syncwarp();
+        col[j] = u;                      // U[j][k]
       }
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k >= lane) a[(c0 + lane) * kDiagLd + c0 + k] = row[k];
+      for (int i = 0; i < 32; ++i)
+        if (i <= lane) a[(c0 + i) * kDiagLd + c0 + lane] = col[i];
     }
     __syncthreads();
     MG_CLK(2 + 3 * kb);
@@ -180,15 +205,17 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
           double x = r[li] * invd[i];
           x = __shfl_sync(0xffffffffu, x, quad_base | owner);
           if (part == owner) r[li] = x;
-          // pivot-row entries U[c0+i][c0 + part*8 .. +8): only the lanes that still have rows
-          // below row i need them
-          if (part * 8 + 7 > i) {
+          // pivot-row entries U[c0+i][c0 + part*8 .. +8): loaded unconditionally (independent of
+          // x, so the loads of later steps run ahead of the substitution chain), applied by select
+          {
             const double2* tp = reinterpret_cast<const double2*>(a + (c0 + i) * kDiagLd + c0 + part * 8);
             const double2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
             const double tv[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
 #pragma unroll
-            for (int l = 0; l < 8; ++l)
-              if (part * 8 + l > i) r[l] = fma(-tv[l], x, r[l]);
+            for (int l = 0; l < 8; ++l) {
+              const double upd = fma(-tv[l], x, r[l]);
+              r[l] = (part * 8 + l > i) ? upd : r[l];
+            }
           }
         }
       }
@@ -203,9 +230,12 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
     // (3) rank-32 update of the trailing upper triangle, 4 x 4 register tiles
     {
       const int nt = rest / 4;       // rest is a multiple of 32
-      for (int e = t; e < nt * nt; e += kPotrfThreads) {
-        const int ti = e / nt, tk = e - ti * nt;
-        if (ti > tk) continue;
+      // only the nt (nt + 1) / 2 tiles on or above the diagonal, packed over the threads
+      for (int e = t; e < nt * (nt + 1) / 2; e += kPotrfThreads) {
+        int tk = static_cast<int>((sqrtf(8.f * static_cast<float>(e) + 1.f) - 1.f) * 0.5f);
+        while (tk * (tk + 1) / 2 > e) --tk;
+        while ((tk + 1) * (tk + 2) / 2 <= e) ++tk;
+        const int ti = e - tk * (tk + 1) / 2;
         const int i0 = c0 + 32 + 4 * ti, k0 = c0 + 32 + 4 * tk;
         double acc[4][4] = {};
 #pragma unroll 4
@@ -239,26 +269,10 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
     if (in && i <= k) A[(j0 + i) * ld + (j0 + k)] = x;
     // forward block: T[m][i] = U[m][i]; identity beyond nb
     t_fwd[i * kTLd + k] = in ? x : (i == k ? 1.f : 0.f);
-    if (in && (u_planes || l_planes)) {
-      __nv_bfloat16 h, m, l;
-      split3(x, h, m, l);
-      if (u_planes) {
-        const int64_t o = (j0 + i) * ld_up + (j0 + k);
-        u_planes[o] = h;
-        u_planes[up_plane_stride + o] = m;
-        u_planes[2 * up_plane_stride + o] = l;
-      }
-      if (l_planes) {
-        const int64_t o = (j0 + k) * ld_up + (j0 + i);
-        l_planes[o] = h;
-        l_planes[up_plane_stride + o] = m;
-        l_planes[2 * up_plane_stride + o] = l;
-      }
-    }
   }
   MG_CLK(19);
   // backward block: T'[m'][i'] = U[nb-1-i'][nb-1-m'] for m' <= i' < nb; identity beyond
-  for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
+  for (int e = t; t_bwd != nullptr && e < kNB * kNB; e += kPotrfThreads) {
     const int mp = e >> 7, ip = e & 127;
     float x = (mp == ip) ? 1.f : 0.f;
     if (mp < nb && ip < nb)
@@ -282,7 +296,7 @@ constexpr int kTrsmCpl = 2;                         // columns per lane: every T
 constexpr int kTrsmThreads = 256;
 constexpr int kTrsmCols = kTrsmThreads / kTrsmLanes * kTrsmCpl;  // 64 columns per block
 constexpr int kXsLd = kNB + 4;                      // xs row stride (floats), 16-byte aligned rows
-constexpr size_t kTrsmSmem = sizeof(float) * (kTBlock + kTrsmCols * kXsLd + kNB);
+constexpr size_t kTrsmSmem = sizeof(float) * (kTBlock + kTrsmCols * kXsLd + kNB) + 16;
 
 __global__ void __launch_bounds__(kTrsmThreads, 2)
     trsm128_kernel(const float* __restrict__ tblock, int reversed, int nb,
@@ -321,20 +335,24 @@ __global__ void __launch_bounds__(kTrsmThreads, 2)
       }
   };
 
-  float rn[kTrsmCpl][kTrsmRows];
-  load_chunk(0, rn);                       // in flight while the triangular block is staged
-  MG_CLK(32);
-  {
-    const float4* src = reinterpret_cast<const float4*>(tblock);
-    float4* dst = reinterpret_cast<float4*>(T);
-    for (int e = tid; e < kTBlock / 4; e += kTrsmThreads) dst[e] = __ldg(src + e);
+  // the triangular block (one contiguous 66 KB record) arrives by a single bulk copy while the
+  // threads fetch their first right-hand-side chunk
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(invd + kNB);
+  if (tid == 0) {
+    mbar_init(tbar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(tbar, static_cast<uint32_t>(sizeof(float) * kTBlock));
+    bulk_load_1d(T, tblock, static_cast<uint32_t>(sizeof(float) * kTBlock), tbar);
   }
-  __syncthreads();
+  float rn[kTrsmCpl][kTrsmRows];
+  load_chunk(0, rn);
+  MG_CLK(32);
+  __syncthreads();                         // barrier initialised before anyone polls it
+  mbar_wait(tbar, 0);
   if (tid < kNB) invd[tid] = 1.f / T[tid * kTLd + tid];
   __syncthreads();
   MG_CLK(33);
 
-  float sumsq[kTrsmCpl] = {0.f, 0.f};
   for (int rb = 0; rb < nchunks; ++rb) {
     float r[kTrsmCpl][kTrsmRows];
 #pragma unroll
@@ -380,80 +398,80 @@ __global__ void __launch_bounds__(kTrsmThreads, 2)
           xs[col_local[q] * kXsLd + ip] = x[q];
         }
       }
-      if (part * kTrsmRows + kTrsmRows - 1 > i) {
+      {
+        // T row loaded unconditionally (it does not depend on x, so later steps' loads run ahead
+        // of the substitution chain) and applied by select to the rows still unsolved
         const float4 ta = *reinterpret_cast<const float4*>(T + ip * kTLd + ip0);
         const float tv[4] = {ta.x, ta.y, ta.z, ta.w};
 #pragma unroll
-        for (int l = 0; l < kTrsmRows; ++l)
-          if (part * kTrsmRows + l > i) {
+        for (int l = 0; l < kTrsmRows; ++l) {
+          const bool below = part * kTrsmRows + l > i;
 #pragma unroll
-            for (int q = 0; q < kTrsmCpl; ++q) r[q][l] = fmaf(-tv[l], x[q], r[q][l]);
+          for (int q = 0; q < kTrsmCpl; ++q) {
+            const float upd = fmaf(-tv[l], x[q], r[q][l]);
+            r[q][l] = below ? upd : r[q][l];
           }
+        }
       }
     }
     __syncwarp();
     MG_CLK(36 + 4 * rb);
-    // ---- outputs of this chunk (this lane's rows of its two columns)
-#pragma unroll
-    for (int q = 0; q < kTrsmCpl; ++q) {
-      if (!valid[q]) continue;
-      float xo[kTrsmRows];
-#pragma unroll
-      for (int i = 0; i < kTrsmRows; ++i) {
-        xo[i] = alpha * r[q][i];
-        if (ip0 + i < nb) sumsq[q] = fmaf(xo[i], xo[i], sumsq[q]);
-      }
-#pragma unroll
-      for (int i = 0; i < kTrsmRows; ++i) {
-        const int ip = ip0 + i;
-        if (ip >= nb) break;
+  }
+  __syncthreads();   // xs[col][ip] now holds every solved (unscaled) entry of this CTA's 64 columns
+
+  // ---- outputs, staged through xs so that every global store is a full-width row segment
+  const int64_t cbase = static_cast<int64_t>(blockIdx.x) * kTrsmCols;
+  {
+    // row-major targets (X, planes): a warp covers 32 consecutive columns of one row
+    const int col = tid & (kTrsmCols - 1), rl = tid / kTrsmCols;
+    const int64_t cg = cbase + col;
+    float ssq = 0.f;
+    if (cg < ncols) {
+      for (int ip = rl; ip < nb; ip += kTrsmThreads / kTrsmCols) {
+        const float xo = alpha * xs[col * kXsLd + ip];
+        ssq = fmaf(xo, xo, ssq);
         const int row = reversed ? nb - 1 - ip : ip;
-        if (X) X[static_cast<int64_t>(row) * ldx + c[q]] = xo[i];
+        if (X) X[static_cast<int64_t>(row) * ldx + cg] = xo;
         if (planes) {
           __nv_bfloat16 h, m, l;
-          split3(xo[i], h, m, l);
-          const int64_t o = static_cast<int64_t>(row) * ldp + c[q];
+          split3(xo, h, m, l);
+          const int64_t o = static_cast<int64_t>(row) * ldp + cg;
           planes[o] = h;
           planes[pstride + o] = m;
           planes[2 * pstride + o] = l;
         }
       }
-      if (tplanes) {
-        __align__(8) __nv_bfloat16 hb[kTrsmRows], mb[kTrsmRows], lb[kTrsmRows];
+    }
+    if (colsumsq) {
+      float* red = T;                      // the triangular block is dead: reuse it
+      red[rl * kTrsmCols + col] = ssq;
+      __syncthreads();
+      if (rl == 0 && cg < ncols) {
+        float v = 0.f;
 #pragma unroll
-        for (int i = 0; i < kTrsmRows; ++i) split3(xo[i], hb[i], mb[i], lb[i]);
-        const int64_t o = c[q] * ldtp + ip0;
-        const bool vec = !reversed && ip0 + kTrsmRows <= nb && ((o & 3) == 0) &&
-                         ((tpstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(tplanes) & 7) == 0);
-        if (vec) {   // 4 bf16 = one 8-byte store per plane
-          *reinterpret_cast<uint2*>(tplanes + o) = *reinterpret_cast<const uint2*>(hb);
-          *reinterpret_cast<uint2*>(tplanes + tpstride + o) = *reinterpret_cast<const uint2*>(mb);
-          *reinterpret_cast<uint2*>(tplanes + 2 * tpstride + o) = *reinterpret_cast<const uint2*>(lb);
-        } else {
-#pragma unroll
-          for (int i = 0; i < kTrsmRows; ++i) {
-            const int ip = ip0 + i;
-            if (ip >= nb) break;
-            const int row = reversed ? nb - 1 - ip : ip;
-            const int64_t oo = c[q] * ldtp + row;
-            tplanes[oo] = hb[i];
-            tplanes[tpstride + oo] = mb[i];
-            tplanes[2 * tpstride + oo] = lb[i];
-          }
-        }
+        for (int q = 0; q < kTrsmThreads / kTrsmCols; ++q) v += red[q * kTrsmCols + col];
+        atomicAdd(colsumsq + cg, v);
+      }
+    }
+  }
+  if (tplanes) {
+    // transposed targets ([col][row]): a warp covers 32 consecutive rows of one column
+    const int ip = tid & (kNB - 1), ch = tid / kNB;
+    if (ip < nb) {
+      const int row = reversed ? nb - 1 - ip : ip;
+      for (int col = ch; col < kTrsmCols; col += kTrsmThreads / kNB) {
+        const int64_t cg = cbase + col;
+        if (cg >= ncols) break;
+        __nv_bfloat16 h, m, l;
+        split3(alpha * xs[col * kXsLd + ip], h, m, l);
+        const int64_t o = cg * ldtp + row;
+        tplanes[o] = h;
+        tplanes[tpstride + o] = m;
+        tplanes[2 * tpstride + o] = l;
       }
     }
   }
   MG_CLK(50);
-  if (colsumsq) {
-#pragma unroll
-    for (int q = 0; q < kTrsmCpl; ++q) {
-      float v = sumsq[q];
-#pragma unroll
-      for (int o = 1; o < kTrsmLanes; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (part == 0 && valid[q]) atomicAdd(colsumsq + c[q], v);
-    }
-  }
 }
 
 }  // namespace
@@ -472,9 +490,8 @@ int split_planes(const float* src, int64_t ld_src, int64_t rows, int64_t cols, _
   return cuda_rc();
 }
 
-int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd,
-             __nv_bfloat16* u_planes, __nv_bfloat16* l_planes, int64_t ld_up,
-             int64_t up_plane_stride, int* info, cudaStream_t s) {
+int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd, int* info,
+             cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -482,8 +499,7 @@ int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bw
     if (e != cudaSuccess) return -1000 - static_cast<int>(e);
     attr_set = true;
   }
-  potrf128_kernel<<<1, kPotrfThreads, kPotrfSmem, s>>>(A, ld, j0, nb, t_fwd, t_bwd, u_planes,
-                                                       l_planes, ld_up, up_plane_stride, info);
+  potrf128_kernel<<<1, kPotrfThreads, kPotrfSmem, s>>>(A, ld, j0, nb, t_fwd, t_bwd, info);
   return cuda_rc();
 }
 
@@ -547,7 +563,7 @@ bool lanes_disabled() {
 int Lanes::bulk_cta_cap() const { return serial ? 0 : device_sm_count() - 4; }
 
 LaneScope::LaneScope(cudaStream_t user) {
-  lanes_.user = lanes_.chain = lanes_.upd = lanes_.tri = user;
+  lanes_.user = lanes_.chain = lanes_.upd = lanes_.tri = lanes_.tri2 = user;
   lanes_.serial = true;
   if (lanes_disabled()) return;
   DeviceLanes& d = device_lanes();
@@ -560,9 +576,12 @@ LaneScope::LaneScope(cudaStream_t user) {
     bool ok = cudaStreamCreateWithPriority(&d.proto.chain, cudaStreamNonBlocking, hi) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&d.proto.upd, cudaStreamNonBlocking, lo) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&d.proto.tri, cudaStreamNonBlocking, lo) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&d.proto.tri2, cudaStreamNonBlocking, lo) == cudaSuccess;
     cudaEvent_t* evs[] = {&d.proto.fork, &d.proto.join[0], &d.proto.join[1], &d.proto.join[2],
                           &d.proto.trsm, &d.proto.upd_done[0], &d.proto.upd_done[1],
-                          &d.proto.misc[0], &d.proto.misc[1]};
+                          &d.proto.misc[0], &d.proto.misc[1], &d.proto.diag_done[0],
+                          &d.proto.diag_done[1], &d.proto.join[3], &d.proto.row_done[0],
+                          &d.proto.row_done[1], &d.proto.bulk_done[0], &d.proto.bulk_done[1]};
     for (cudaEvent_t* e : evs)
       ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) cudaGetLastError();
@@ -576,12 +595,13 @@ LaneScope::LaneScope(cudaStream_t user) {
   cudaStreamWaitEvent(lanes_.chain, lanes_.fork, 0);
   cudaStreamWaitEvent(lanes_.upd, lanes_.fork, 0);
   cudaStreamWaitEvent(lanes_.tri, lanes_.fork, 0);
+  cudaStreamWaitEvent(lanes_.tri2, lanes_.fork, 0);
 }
 
 LaneScope::~LaneScope() {
   if (!lanes_.serial) {
-    cudaStream_t ls[3] = {lanes_.chain, lanes_.upd, lanes_.tri};
-    for (int i = 0; i < 3; ++i) {
+    cudaStream_t ls[4] = {lanes_.chain, lanes_.upd, lanes_.tri, lanes_.tri2};
+    for (int i = 0; i < 4; ++i) {
       cudaEventRecord(lanes_.join[i], ls[i]);
       cudaStreamWaitEvent(lanes_.user, lanes_.join[i], 0);
     }
@@ -599,10 +619,10 @@ int CholStepper::step(int64_t pj) const {
   const int64_t j0 = pj * kNB;
   const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
   float* tf = ws.t_fwd + pj * kTBlock;
-  float* tb = ws.t_bwd + pj * kTBlock;
+  float* tb = ws.t_bwd ? ws.t_bwd + pj * kTBlock : nullptr;   // only back-substitutions need it
   int rc;
   MG_TIMED(L.chain, "chol.potrf128",
-           rc = potrf128(A, ld, j0, nb, tf, tb, ws.u_planes, ws.l_planes, np, pstride, info, L.chain));
+           rc = potrf128(A, ld, j0, nb, tf, tb, info, L.chain));
   if (rc) return rc;
   const int64_t rest = n - j0 - nb;
   if (rest <= 0) {

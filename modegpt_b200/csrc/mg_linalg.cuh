@@ -29,12 +29,11 @@ int split_planes(const float* src, int64_t ld_src, int64_t rows, int64_t cols, _
 // Also emits
 //   t_fwd [128 x 132] fp32 : T[m][i] = U11[m][i]                (solves U11^T x = b)
 //   t_bwd [128 x 132] fp32 : T[m'][i'] = U11[nb-1-i'][nb-1-m']  (solves U11 x = b, reversed rows)
-// both identity-padded beyond nb, and (optionally) bf16 planes of U11 / U11^T at the block's
-// coordinates inside u_planes / l_planes (leading dimension ld_up).
+// both identity-padded beyond nb.  (No bf16 planes: every tensor-core product of the blocked
+// drivers reads block rows strictly outside the diagonal blocks.)
 // A non-positive pivot records its 1-based global index in *info (first failure wins).
-int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd,
-             __nv_bfloat16* u_planes, __nv_bfloat16* l_planes, int64_t ld_up,
-             int64_t up_plane_stride, int* info, cudaStream_t s);
+int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd, int* info,
+             cudaStream_t s);
 
 // Triangular solve with one compact 128-block against many right-hand-side columns, one thread
 // per column:  X = alpha * T^-1 B  where T is t_fwd (rows in natural order) or t_bwd (reversed).

@@ -41,7 +41,7 @@ struct Carver {
 
 struct ScoresWs {
   float* a;          // [n x np] working copy C + ridge I -> U
-  float* tt;         // [128 x np]
+  float* tt;         // [2][128 x np]
   float* ident;      // [128 x 128] identity (right-hand side for the diagonal blocks of U^-T)
   bf16* y_planes;    // [3][np x np]
   mg::CholWorkspace chol;
@@ -54,13 +54,13 @@ ScoresWs carve_scores(void* p, int64_t n) {
   Carver c(p);
   ScoresWs w{};
   w.a = c.take<float>(n * np);
-  w.tt = c.take<float>(kNB * np);
+  w.tt = c.take<float>(2 * kNB * np);   // double-buffered (look-ahead on the tri lanes)
   w.ident = c.take<float>(kNB * kNB);
   w.y_planes = c.take<bf16>(kPlanes * np * np);
   w.chol.u_planes = c.take<bf16>(kPlanes * np * np);
   w.chol.l_planes = nullptr;
   w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
-  w.chol.t_bwd = c.take<float>(panels * mg::kTBlock);
+  w.chol.t_bwd = nullptr;   // no back-substitution on this path
   w.chol.n_pad = np;
   w.bytes = c.off + 256;
   return w;
@@ -71,7 +71,7 @@ struct NystromWs {
   bf16* wdt;        // [n x dp]        W_down^T
   float* rhs;       // [k x dp]        cross term -> Z -> X (in place)
   float* ckk;       // [k x kp]
-  bf16* z_planes;   // [3][128 x dp]
+  bf16* z_planes;   // [2][3][128 x dp]
   mg::CholWorkspace chol;
   size_t bytes;
 };
@@ -85,7 +85,7 @@ NystromWs carve_nystrom(void* p, int64_t n, int64_t k, int64_t d) {
   w.wdt = c.take<bf16>(n * dp);
   w.rhs = c.take<float>(k * dp);
   w.ckk = c.take<float>(k * kp);
-  w.z_planes = c.take<bf16>(kPlanes * kNB * dp);
+  w.z_planes = c.take<bf16>(2 * kPlanes * kNB * dp);   // double-buffered: look-ahead overlaps two panels
   w.chol.u_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.l_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
@@ -332,49 +332,86 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
   const int64_t pstride = np * np;
   identity_kernel<<<(kNB * kNB + 255) / 256, 256, 0, L.tri>>>(w.ident, kNB);
   if ((rc = cuda_rc())) return rc;
+  L.record(L.misc[0], L.tri);
 
   mg::CholStepper chol{w.a, n, np, w.chol, info, &L};
   for (int64_t j0 = 0, pj = 0; j0 < n; j0 += kNB, ++pj) {
     if ((rc = chol.step(pj))) return rc;
-    L.wait(L.tri, L.trsm);
     const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
     const float* tf = w.chol.t_fwd + pj * mg::kTBlock;
-    // diagonal block Y[jb, jb] = U_jj^-T (solve U_jj^T X = I)
-    MG_TIMED(L.tri, "trtri.diag_trsm", rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
+    // diagonal block Y[jb, jb] = U_jj^-T (solve U_jj^T X = I): two CTAs of pure latency, so it
+    // rides on the upd lane (which has slack) instead of lengthening the tri lane's own chain
+    if (pj == 0) L.wait(L.upd, L.misc[0]);   // scores / y_planes are cleared on the tri lane
+    L.wait(L.upd, L.trsm);
+    MG_TIMED(L.upd, "trtri.diag_trsm", rc = mg::trsm128(tf, false, nb, w.ident, kNB, nb, 1.f, nullptr, 0,
                                                         w.y_planes + j0 * np + j0, np, pstride, nullptr, 0, 0,
-                                                        scores + j0, L.tri));
+                                                        scores + j0, L.upd));
     if (rc) return rc;
-    if (j0 == 0) continue;
-    // Tt[nb, j0] = U[0:j0, jb]^T * Y[0:j0, 0:j0]
-    cudaMemsetAsync(w.tt, 0, sizeof(float) * kNB * np, L.tri);
+    L.record(L.diag_done[pj & 1], L.upd);
+    if (j0 == 0) {
+      L.record(L.row_done[0], L.tri);
+      continue;
+    }
+    // Tt[nb, j0] = U[0:j0, jb]^T * Y[0:j0, 0:j0], split by the rows of Y it needs:
+    //   bulk (tri2 lane): block rows <= pj-2 of Y — everything except the row finished last, so it
+    //                     overlaps the previous row's triangular solve;
+    //   tail (tri lane) : block row pj-1 of Y (K = 128), added on top once bulk has landed.
+    float* tt = w.tt + (pj & 1) * kNB * np;
     mg::GemmArgs g{};
-    g.A = w.chol.u_planes + j0;
     g.lda = np;
     g.a_plane_stride = pstride;
     g.a_planes = kPlanes;
-    g.B = w.y_planes;
     g.ldb = np;
     g.b_plane_stride = pstride;
     g.b_planes = kPlanes;
     pairs6(g);
     g.M = nb;
     g.N = j0;
-    g.K = j0;
-    g.D = w.tt;
+    g.D = tt;
     g.ldd = np;
     g.alpha = 1.f;
     g.tiles = mg::TILES_FULL;
     g.epi = mg::EPI_ADD;
-    g.ksplit = 0;
-    g.klo_from_n = 1;
     g.max_ctas = L.bulk_cta_cap();
-    MG_TIMED(L.tri, "trtri.gemm1", rc = mg::gemm_tn_launch(g, L.tri));
-    if (rc) return rc;
+    const int64_t kbulk = L.serial ? j0 : j0 - kNB;     // j0 is a multiple of 128
+    cudaStream_t sb = kbulk > 0 ? L.tri2 : L.tri;
+    if (kbulk > 0) {
+      L.wait(L.tri2, L.trsm);                            // block row pj of U
+      if (pj >= 2) L.wait(L.tri2, L.row_done[(pj - 2) & 1]);   // rows <= pj-2 of Y; tt[pj&1] is free
+      L.wait(L.tri2, L.diag_done[(pj - 1) & 1]);        // (serial: no-op) diagonal blocks < pj
+    }
+    cudaMemsetAsync(tt, 0, sizeof(float) * kNB * np, sb);
+    if (kbulk > 0) {
+      mg::GemmArgs b = g;
+      b.A = w.chol.u_planes + j0;
+      b.B = w.y_planes;
+      b.K = kbulk;
+      b.ksplit = 0;
+      b.klo_from_n = 1;
+      MG_TIMED(L.tri2, "trtri.gemm_bulk", rc = mg::gemm_tn_launch(b, L.tri2));
+      if (rc) return rc;
+      L.record(L.bulk_done[pj & 1], L.tri2);
+    }
+    L.wait(L.tri, L.trsm);
+    L.wait(L.tri, L.diag_done[(pj - 1) & 1]);
+    if (kbulk > 0) L.wait(L.tri, L.bulk_done[pj & 1]);
+    if (!L.serial) {
+      mg::GemmArgs tl = g;
+      tl.A = w.chol.u_planes + (j0 - kNB) * np + j0;
+      tl.B = w.y_planes + (j0 - kNB) * np;
+      tl.K = kNB;
+      tl.ksplit = 1;
+      tl.klo_from_n = 0;
+      tl.max_ctas = 0;
+      MG_TIMED(L.tri, "trtri.gemm_tail", rc = mg::gemm_tn_launch(tl, L.tri));
+      if (rc) return rc;
+    }
     // Y[jb, 0:j0] = -U_jj^-T Tt : planes + column sums of squares in one pass
-    MG_TIMED(L.tri, "trtri.row_trsm", rc = mg::trsm128(tf, false, nb, w.tt, np, j0, -1.f, nullptr, 0,
+    MG_TIMED(L.tri, "trtri.row_trsm", rc = mg::trsm128(tf, false, nb, tt, np, j0, -1.f, nullptr, 0,
                                                        w.y_planes + j0 * np, np, pstride, nullptr, 0, 0,
                                                        scores, L.tri));
     if (rc) return rc;
+    L.record(L.row_done[pj & 1], L.tri);
   }
   mg::Prof::get().report(s, "mg_ridge_scores_f32");
   return 0;
@@ -529,37 +566,56 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   L.wait(L.chain, L.misc[0]);
   L.record(L.misc[1], L.upd);
   L.wait(L.chain, L.misc[1]);
-  for (int64_t pi = panels - 1; pi >= 0; --pi) {
+  //      Same look-ahead as the factorisation: the chain lane updates only the block row the next
+  //      back-substitution needs, the upd lane the rows above it.
+  for (int64_t pi = panels - 1, it = 0; pi >= 0; --pi, ++it) {
     const int64_t i0 = pi * kNB;
     const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
     float* zi = w.rhs + i0 * dp;
     MG_TIMED(L.chain, "nystrom.bwd_trsm",
              rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
-                              i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
-                              L.chain));
+                              i0 > 0 ? w.z_planes + (it & 1) * kPlanes * kNB * dp : nullptr, dp, kNB * dp,
+                              nullptr, 0, 0, nullptr, L.chain));
     if (rc) return rc;
     if (i0 == 0) break;
+    L.record(L.trsm, L.chain);
     mg::GemmArgs t{};
-    t.A = w.chol.l_planes + i0 * kp;  // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
     t.lda = kp;
     t.a_plane_stride = pstride;
     t.a_planes = kPlanes;
-    t.B = w.z_planes;
+    t.B = w.z_planes + (it & 1) * kPlanes * kNB * dp;
     t.ldb = dp;
     t.b_plane_stride = kNB * dp;
     t.b_planes = kPlanes;
     pairs6(t);
-    t.M = i0;
     t.N = d;
     t.K = nb;
-    t.D = w.rhs;
     t.ldd = dp;
     t.alpha = -1.f;
     t.tiles = mg::TILES_FULL;
     t.epi = mg::EPI_ADD;
     t.ksplit = 1;
-    MG_TIMED(L.chain, "nystrom.bwd_update", rc = mg::gemm_tn_launch(t, L.chain));
-    if (rc) return rc;
+    // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
+    const int64_t m1 = L.serial ? 0 : kNB;          // i0 is a multiple of 128
+    if (i0 - m1 > 0) {
+      mg::GemmArgs r = t;
+      r.A = w.chol.l_planes + i0 * kp;
+      r.M = i0 - m1;
+      r.D = w.rhs;
+      r.max_ctas = L.bulk_cta_cap();
+      L.wait(L.upd, L.trsm);
+      MG_TIMED(L.upd, "nystrom.bwd_update", rc = mg::gemm_tn_launch(r, L.upd));
+      if (rc) return rc;
+      L.record(L.upd_done[it & 1], L.upd);
+    }
+    if (m1 > 0) {
+      if (it >= 1) L.wait(L.chain, L.upd_done[(it - 1) & 1]);   // ordered adds into block row pi-1
+      t.A = w.chol.l_planes + i0 * kp + (i0 - m1);
+      t.M = m1;
+      t.D = w.rhs + (i0 - m1) * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_row_update", rc = mg::gemm_tn_launch(t, L.chain));
+      if (rc) return rc;
+    }
   }
   // ---- W_down' [d, k] = X^T, bf16
   transpose_to_bf16_kernel<float><<<dim3(static_cast<unsigned>((d + 31) / 32),

@@ -179,27 +179,33 @@ __device__ void jacobi_eig(EigSmem& s, int hd) {
         s.pq[2 * t + 1] = q;
       }
       __syncthreads();
-      // columns: G <- G J, V <- V J
+      // G <- J^T G J in one pass: the 64 x 64 pair blocks {p_k,q_k} x {p_l,q_l} are disjoint, so
+      // each 2 x 2 block is read, rotated on both sides and written back by one thread
+      for (int e = t; e < half * half; e += nt) {
+        const int k = e / half, l = e - k * half;
+        const int pk = s.pq[2 * k], qk = s.pq[2 * k + 1];
+        const int pl = s.pq[2 * l], ql = s.pq[2 * l + 1];
+        const double ck = s.cs[2 * k], sk = s.cs[2 * k + 1];
+        const double cl = s.cs[2 * l], sl = s.cs[2 * l + 1];
+        const double gpp = s.g[pk * ld + pl], gpq = s.g[pk * ld + ql];
+        const double gqp = s.g[qk * ld + pl], gqq = s.g[qk * ld + ql];
+        // right rotation (columns pl, ql)
+        const double a_pp = cl * gpp - sl * gpq, a_pq = sl * gpp + cl * gpq;
+        const double a_qp = cl * gqp - sl * gqq, a_qq = sl * gqp + cl * gqq;
+        // left rotation (rows pk, qk)
+        s.g[pk * ld + pl] = ck * a_pp - sk * a_qp;
+        s.g[pk * ld + ql] = ck * a_pq - sk * a_qq;
+        s.g[qk * ld + pl] = sk * a_pp + ck * a_qp;
+        s.g[qk * ld + ql] = sk * a_pq + ck * a_qq;
+      }
+      // V <- V J
       for (int e = t; e < hd * half; e += nt) {
         const int k = e / hd, i = e - k * hd;
         const int p = s.pq[2 * k], q = s.pq[2 * k + 1];
         const double c = s.cs[2 * k], sn = s.cs[2 * k + 1];
-        const double gp = s.g[i * ld + p], gq = s.g[i * ld + q];
-        s.g[i * ld + p] = c * gp - sn * gq;
-        s.g[i * ld + q] = sn * gp + c * gq;
         const float vp = s.v[i * ld + p], vq = s.v[i * ld + q];
         s.v[i * ld + p] = static_cast<float>(c * vp - sn * vq);
         s.v[i * ld + q] = static_cast<float>(sn * vp + c * vq);
-      }
-      __syncthreads();
-      // rows: G <- J^T G
-      for (int e = t; e < hd * half; e += nt) {
-        const int k = e / hd, j = e - k * hd;
-        const int p = s.pq[2 * k], q = s.pq[2 * k + 1];
-        const double c = s.cs[2 * k], sn = s.cs[2 * k + 1];
-        const double gp = s.g[p * ld + j], gq = s.g[q * ld + j];
-        s.g[p * ld + j] = c * gp - sn * gq;
-        s.g[q * ld + j] = sn * gp + c * gq;
       }
       __syncthreads();
     }

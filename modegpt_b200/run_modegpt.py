@@ -74,7 +74,7 @@ def main(trial=None, config: CompressionConfig | None = None):
     n_layers = adapter.n_layers
     save_dir = os.path.join(config.output_dir, "model")
     rotary_masks: list = []
-    timings = {"calibration_s": 0.0, "mlp_s": 0.0, "qk_s": 0.0, "vo_s": 0.0}
+    timings = {"calibration_s": 0.0, "mlp_s": 0.0, "qk_s": 0.0, "vo_s": 0.0, "file_flush_s": 0.0}
 
     def timed(key, fn):
         torch.cuda.synchronize()
@@ -134,11 +134,14 @@ def main(trial=None, config: CompressionConfig | None = None):
         gc.collect()
         torch.cuda.empty_cache()
 
+    # the layer files are written behind the decompositions (handoff.LayerWriter); the wait for the
+    # last of them belongs to the compression stage ("compress s/layer incl. file write")
+    timed("file_flush_s", adapter.flush_saves)
     D.barrier()   # every owner has written its layer files
     tokens = config.calib_size * config.seq_len
     adapter.metrics.update({**timings, "calib_tokens_per_s": tokens / max(timings["calibration_s"], 1e-9),
-                            "compress_s_per_layer": (timings["mlp_s"] + timings["qk_s"]
-                                                     + timings["vo_s"]) / n_layers,
+                            "compress_s_per_layer": (timings["mlp_s"] + timings["qk_s"] + timings["vo_s"]
+                                                     + timings["file_flush_s"]) / n_layers,
                             "world_size": D.world_size()})
     if not is_root:
         return None

@@ -158,3 +158,37 @@ def test_adapter_tables_resolve_on_tiny_models():
         assert a.get_qk_tensors(0).query_proj.shape == (256, 256)
         assert a.get_vo_tensors(2).o_proj.shape[0] == 256
         assert a.n_kv_heads == (2 if "gqa" in preset or "qwen" in preset else 4)
+
+
+def test_layer_writer_files_match_blocking_save(tmp_path):
+    """handoff.LayerWriter writes the same `torch.load`-able dicts the reference's blocking
+    torch.save produces (file names and keys unchanged), including non-contiguous views, and
+    surfaces writer errors in flush()."""
+    import torch
+
+    from modegpt_b200.handoff import LayerWriter
+
+    g = torch.Generator().manual_seed(3)
+    w = LayerWriter(n_threads=2, n_buffers=2)
+    expect = {}
+    for i in range(6):
+        d = {"up": torch.randn(8 + i, 16, generator=g).bfloat16(),
+             "down": torch.randn(16, 8 + i, generator=g).bfloat16().T,     # transposed view
+             "mask": torch.arange(5 + i)}
+        path = tmp_path / "layers" / f"layer_{i}_mlp"
+        w.submit(str(path), d)
+        expect[path] = d
+    w.flush()
+    for path, d in expect.items():
+        got = torch.load(path)
+        assert set(got) == set(d)
+        for k in d:
+            assert got[k].dtype == d[k].dtype and torch.equal(got[k], d[k])
+        # a private storage per tensor, not the staging buffer
+        assert got["up"].untyped_storage().nbytes() == got["up"].numel() * 2
+    bad = tmp_path / "file_not_dir"
+    bad.write_text("x")
+    w.submit(str(bad / "layer_0_mlp"), {"up": torch.zeros(2)})
+    with pytest.raises(RuntimeError):
+        w.flush()
+    w.close()

@@ -335,7 +335,8 @@ def test_type1_lanes_match_single_stream(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         res[tag] = torch.load(path)
     a, b = res["lanes"], res["serial"]
-    assert torch.equal(a["c"], b["c"])            # same tiles, same K order: bit-identical statistics
+    # same tiles and K order; only the order of the split-K partial sums in L2 is free
+    assert rel(a["c"].numpy(), b["c"].numpy()) < 1e-6
     assert rel(a["s"].numpy(), b["s"].numpy()) < 1e-5
     assert torch.equal(a["idx"], b["idx"])
     assert rel(a["out"].numpy(), b["out"].numpy()) < 2e-3
@@ -344,13 +345,17 @@ def test_type1_lanes_match_single_stream(tmp_path):
     assert rel(a["s"].numpy(), ref) < 1e-3
 
 
-def test_type1_repeated_calls_are_deterministic(ops):
-    """Lane hand-offs are ordered by events (no racing L2 reduce-adds): same bits every call."""
+def test_type1_repeated_calls_agree(ops):
+    """Lane hand-offs are ordered by events: repeated calls agree to the split-K summation noise
+    and select the same columns."""
     n = 1160
     x = shaped(3000, n, seed=11).to(DEV)
     c = torch.zeros(n, n, device=DEV)
     ops.syrk_(c, x)
     ops.finalize_sym_(c, 1.0 / 3000)
     first = ops.ridge_scores(c, 1e-3)
+    idx = ops.select_k(first, 800)
     for _ in range(3):
-        assert torch.equal(ops.ridge_scores(c, 1e-3), first)
+        again = ops.ridge_scores(c, 1e-3)
+        assert rel(again.cpu().numpy(), first.cpu().numpy()) < 1e-6
+        assert torch.equal(ops.select_k(again, 800), idx)
