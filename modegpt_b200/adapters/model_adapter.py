@@ -366,16 +366,21 @@ class ModelAdapter(ABC):
             os.makedirs(output_dir, exist_ok=True)
             torch.save(weights, path)
             return
-        if self._writer is None:
-            from ..handoff import LayerWriter
-
-            self._writer = LayerWriter()
+        self.prepare_writer()
         self._writer.submit(path, weights)
         first = next(iter(weights.values()))
         if first.is_cuda:
             free, total = torch.cuda.mem_get_info(first.device)
             if free > 0.3 * total:
                 self._layer_cache[(int(layer_idx), suffix)] = weights
+
+    def prepare_writer(self) -> None:
+        """Create the asynchronous layer writer (handoff.LayerWriter) on first use."""
+        if self._writer is not None or self.config.keep_layers_in_memory or self.config.sync_save:
+            return
+        from ..handoff import LayerWriter
+
+        self._writer = LayerWriter()
 
     def flush_saves(self) -> None:
         """Block until every submitted layer file is on disk (raises if a write failed)."""

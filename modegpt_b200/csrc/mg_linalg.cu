@@ -44,6 +44,14 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
   return y;
 }
 
+// D (8 x 8, fp64) += A (8 x 4, row) * B (4 x 8, col) on the FP64 tensor cores; per-thread fragments:
+// a = A[lane >> 2][lane & 3], b = B[lane & 3][lane >> 2], (d0, d1) = D[lane >> 2][2 (lane & 3) + {0, 1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 // ---------------------------------------------------------------------------------------------
 // split kernel: 32 x 64 tile per block, 256 threads (64 columns x 4 row lanes)
 // ---------------------------------------------------------------------------------------------
@@ -188,73 +196,56 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
     }
     __syncthreads();
     MG_CLK(2 + 3 * kb);
-    // (2) block row: forward substitution, a quad of lanes per column (lane `part` owns 8 rows)
+    // (2) block row: forward substitution, one thread per column with the 32 rows in registers.
+    //     The triangular coefficients U[c0+i][c0+l] are the same for every column (broadcast
+    //     16-byte loads, independent of the running solution), so per column the chain is just
+    //     32 x (multiply, fused multiply-add); no shuffles, no intermediate barrier.
     const int rest = kNB - c0 - 32;  // columns right of the sub-panel (padding included)
-    {
-      const int cl = t >> 2, part = t & 3;
-      const int quad_base = lane & ~3;
-      const bool active = cl < rest;           // rest is a multiple of 32: warps are uniform
-      const int k = c0 + 32 + cl;
-      double r[8];
-      if (active) {
+    if (t < rest) {
+      const int k = c0 + 32 + t;
+      double r[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = a[(c0 + part * 8 + i) * kDiagLd + k];
+      for (int i = 0; i < 32; ++i) r[i] = a[(c0 + i) * kDiagLd + k];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int owner = i >> 3, li = i & 7;
-          double x = r[li] * invd[i];
-          x = __shfl_sync(0xffffffffu, x, quad_base | owner);
-          if (part == owner) r[li] = x;
-          // pivot-row entries U[c0+i][c0 + part*8 .. +8): loaded unconditionally (independent of
-          // x, so the loads of later steps run ahead of the substitution chain), applied by select
-          {
-            const double2* tp = reinterpret_cast<const double2*>(a + (c0 + i) * kDiagLd + c0 + part * 8);
-            const double2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
-            const double tv[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
+      for (int i = 0; i < 32; ++i) {
+        const double x = r[i] * invd[i];
+        r[i] = x;
+        const double* trow = a + (c0 + i) * kDiagLd + c0;
 #pragma unroll
-            for (int l = 0; l < 8; ++l) {
-              const double upd = fma(-tv[l], x, r[l]);
-              r[l] = (part * 8 + l > i) ? upd : r[l];
-            }
-          }
+        for (int l2 = (i + 1) / 2; l2 < 16; ++l2) {
+          const double2 tv = *reinterpret_cast<const double2*>(trow + 2 * l2);
+          if (2 * l2 > i) r[2 * l2] = fma(-tv.x, x, r[2 * l2]);
+          r[2 * l2 + 1] = fma(-tv.y, x, r[2 * l2 + 1]);
         }
       }
-      __syncthreads();   // every read of the old block row is done
-      if (active) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[(c0 + part * 8 + i) * kDiagLd + k] = r[i];
-      }
+      for (int i = 0; i < 32; ++i) a[(c0 + i) * kDiagLd + k] = r[i];
     }
     __syncthreads();
     MG_CLK(3 + 3 * kb);
-    // (3) rank-32 update of the trailing upper triangle, 4 x 4 register tiles
+    // (3) rank-32 update of the trailing upper triangle on the FP64 tensor cores: 8 x 8 tiles of
+    //     A22 -= U12^T U12, eight mma.m8n8k4 per tile, tiles on or above the diagonal dealt to the
+    //     16 warps.  Fragment coordinates: A[i][m] and B[m][k] are both read from row c0+m of the
+    //     block (thread: m = lane & 3, i or k = lane >> 2); C rows lane >> 2, columns 2 (lane & 3).
     {
-      const int nt = rest / 4;       // rest is a multiple of 32
-      // only the nt (nt + 1) / 2 tiles on or above the diagonal, packed over the threads
-      for (int e = t; e < nt * (nt + 1) / 2; e += kPotrfThreads) {
+      const int nt = rest / 8;       // rest is a multiple of 32
+      const int fm = lane & 3, fr = lane >> 2;
+      for (int e = warp; e < nt * (nt + 1) / 2; e += kPotrfThreads / 32) {
         int tk = static_cast<int>((sqrtf(8.f * static_cast<float>(e) + 1.f) - 1.f) * 0.5f);
         while (tk * (tk + 1) / 2 > e) --tk;
         while ((tk + 1) * (tk + 2) / 2 <= e) ++tk;
         const int ti = e - tk * (tk + 1) / 2;
-        const int i0 = c0 + 32 + 4 * ti, k0 = c0 + 32 + 4 * tk;
-        double acc[4][4] = {};
-#pragma unroll 4
-        for (int m = 0; m < 32; ++m) {
-          const double2* pi = reinterpret_cast<const double2*>(a + (c0 + m) * kDiagLd + i0);
-          const double2* pk = reinterpret_cast<const double2*>(a + (c0 + m) * kDiagLd + k0);
-          const double2 i01 = pi[0], i23 = pi[1], k01 = pk[0], k23 = pk[1];
-          const double ui[4] = {i01.x, i01.y, i23.x, i23.y};
-          const double uk[4] = {k01.x, k01.y, k23.x, k23.y};
+        const int i0 = c0 + 32 + 8 * ti, k0 = c0 + 32 + 8 * tk;
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fma(ui[x], uk[y], acc[x][y]);
+        for (int m0 = 0; m0 < 32; m0 += 4) {
+          const double av = a[(c0 + m0 + fm) * kDiagLd + i0 + fr];
+          const double bv = a[(c0 + m0 + fm) * kDiagLd + k0 + fr];
+          dmma_m8n8k4(acc0, acc1, av, bv);
         }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y)
-            if (i0 + x <= k0 + y) a[(i0 + x) * kDiagLd + k0 + y] -= acc[x][y];
+        const int row = i0 + fr, colb = k0 + 2 * fm;
+        if (row <= colb) a[row * kDiagLd + colb] -= acc0;
+        if (row <= colb + 1) a[row * kDiagLd + colb + 1] -= acc1;
       }
     }
     __syncthreads();

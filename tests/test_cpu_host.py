@@ -169,7 +169,7 @@ def test_layer_writer_files_match_blocking_save(tmp_path):
     from modegpt_b200.handoff import LayerWriter
 
     g = torch.Generator().manual_seed(3)
-    w = LayerWriter(n_threads=2, n_buffers=2)
+    w = LayerWriter(n_threads=2, max_in_flight=2)
     expect = {}
     for i in range(6):
         d = {"up": torch.randn(8 + i, 16, generator=g).bfloat16(),
@@ -184,8 +184,6 @@ def test_layer_writer_files_match_blocking_save(tmp_path):
         assert set(got) == set(d)
         for k in d:
             assert got[k].dtype == d[k].dtype and torch.equal(got[k], d[k])
-        # a private storage per tensor, not the staging buffer
-        assert got["up"].untyped_storage().nbytes() == got["up"].numel() * 2
     bad = tmp_path / "file_not_dir"
     bad.write_text("x")
     w.submit(str(bad / "layer_0_mlp"), {"up": torch.zeros(2)})
