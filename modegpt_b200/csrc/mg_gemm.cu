@@ -7,7 +7,8 @@
 // Kernel shape (one CTA per SM, persistent over work items):
 //   warp 0      : TMA producer   — 64-column x BK-row boxes, SWIZZLE_128B, 3D maps (col,row,plane)
 //   warp 1      : MMA issuer     — tcgen05.mma 128 x BN x 16, both operands MN-major, fp32 in TMEM
-//   warps 2..5  : epilogue       — tcgen05.ld 32x32b, fused accumulate / triangular predication
+//   warps 2..9  : epilogue       — tcgen05.ld 32x32b, fused accumulate / triangular predication
+//                 (two warps per TMEM lane quadrant, each draining half of the columns)
 // TMEM holds two accumulators (2 x BN columns) so the epilogue of tile i overlaps tile i+1.
 #include "mg_gemm.cuh"
 
@@ -27,15 +28,16 @@ constexpr int BK = 64;
 constexpr int kChunkCols = 64;                    // one TMA box = 64 bf16 = 128 B wide
 constexpr uint32_t kBoxBytes = BK * 128;          // 8 KB
 constexpr uint32_t kABytes = (BM / 64) * kBoxBytes;  // 16 KB
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quadrant, half the columns each
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 
 template <int BN>
 struct Cfg {
   static constexpr uint32_t b_bytes = (BN / 64) * kBoxBytes;
   static constexpr uint32_t stage_bytes = kABytes + b_bytes;
   static constexpr int stages = (BN == 256) ? 4 : 6;
-  static constexpr uint32_t epi_bytes = 4 * 2 * 4096;  // per epilogue warp: 2 x (32 x 32 fp32)
+  static constexpr uint32_t epi_bytes = kEpiWarps * 4096;  // per epilogue warp: one 32 x 32 fp32 tile
   static constexpr uint32_t smem_bytes = stages * stage_bytes + epi_bytes + 1024 + 512;
 };
 
@@ -237,8 +239,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue (8 warps)
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int chalf = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
+    constexpr int kChunksPerWarp = BN / 64;
+    const int cc_lo = chalf * kChunksPerWarp, cc_hi = cc_lo + kChunksPerWarp;
     const int row_in_tile = q * 32 + lane;
     int it = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -256,10 +261,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         // TMEM -> registers -> 128B-swizzled staging tile -> TMA store / L2 reduce-add.
         // TMA clips at the tensor bounds; in TILES_UPPER chunks that straddle the diagonal are
         // written whole (the strict lower triangle is unspecified by contract).
-        uint8_t* wbuf = epi_smem + (warp - 2) * 8192;
+        uint8_t* buf = epi_smem + (warp - 2) * 4096;
         if (warp_row0 < p.M) {
 #pragma unroll 1
-          for (int cc = 0; cc < BN / 32; ++cc) {
+          for (int cc = cc_lo; cc < cc_hi; ++cc) {
             const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
             if (gc0 >= p.N) break;
             if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
@@ -268,8 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                    static_cast<uint32_t>(as * BN + cc * 32);
             tmem_ld_32x32(taddr, v);
             tmem_ld_wait();
-            uint8_t* buf = wbuf + (cc & 1) * 4096;
-            if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has read `buf`
+            if (lane == 0) bulk_wait_read<0>();  // the previous store has read `buf`
             __syncwarp();
             uint8_t* rowp = buf + lane * 128;
 #pragma unroll
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         continue;
       }
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
+      for (int cc = cc_lo; cc < cc_hi; ++cc) {
         const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
         // warp-uniform skips: chunk entirely out of range / strictly below the diagonal /
         // outside this warp's head block.
@@ -402,13 +406,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 //   * each CTA drains its own 128 TMEM lanes through the same TMA store / reduce-add epilogue and
 //     releases the accumulator by a remote arrive on the leader's `tmem_empty` barrier.
 // ------------------------------------------------------------------------------------------------
+//   * eight epilogue warps per CTA (two per TMEM lane quadrant, 128 accumulator columns each): with
+//     four, a K = 128 x 6-plane trailing update spent 9 us per tile draining 8 chunks per warp
+//     against 5.3 us of MMA (tensor pipe 44 % in ncu); halving the chunks per warp puts the drain
+//     back under the main loop.
 constexpr int kPairBM = 256, kPairBN = 256;
 constexpr int kPairStages = 6;
 constexpr uint32_t kPairStageBytes = 2 * kABytes;   // 16 KB of A + 16 KB of B per CTA
-constexpr uint32_t kPairEpiBytes = 4 * 2 * 4096;
+constexpr int kPairEpiWarps = 8;
+constexpr int kPairEpiThreads = kPairEpiWarps * 32;
+constexpr int kPairThreads = 64 + kPairEpiThreads;
+static_assert(kPairThreads == kThreads, "both kernels use two service warps + eight epilogue warps");
+constexpr uint32_t kPairEpiBytes = kPairEpiWarps * 4096;   // one 32 x 32 fp32 staging tile per warp
 constexpr uint32_t kPairSmem = kPairStages * kPairStageBytes + kPairEpiBytes + 1024 + 512;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
     gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmD, const KParams p) {
@@ -439,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 2 * kEpiThreads);   // epilogue threads of BOTH CTAs
+      mbar_init(&tmem_empty[s], 2 * kPairEpiThreads);   // epilogue threads of BOTH CTAs
     }
     fence_barrier_init();
   }
@@ -527,8 +539,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs)
-    const int q = warp & 3;
-    uint8_t* wbuf = epi_smem + (warp - 2) * 8192;
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int chalf = (warp - 2) >> 2;            // which 128 accumulator columns it drains
+    uint8_t* buf = epi_smem + (warp - 2) * 4096;
     int it = 0;
     for (int w = cluster_id; w < p.total_work; w += n_clusters) {
       const Work wk = decode_work<kPairBN, kPairBM>(p, w);
@@ -541,7 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int64_t warp_row0 = static_cast<int64_t>(wk.mi) * kPairBM + rank * 128 + q * 32;
       if (warp_row0 < p.M) {
 #pragma unroll 1
-        for (int cc = 0; cc < kPairBN / 32; ++cc) {
+        for (int cc = chalf * 4; cc < chalf * 4 + 4; ++cc) {
           const int64_t gc0 = static_cast<int64_t>(wk.nj) * kPairBN + cc * 32;
           if (gc0 >= p.N) break;
           if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
@@ -550,8 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                  static_cast<uint32_t>(as * kPairBN + cc * 32);
           tmem_ld_32x32(taddr, v);
           tmem_ld_wait();
-          uint8_t* buf = wbuf + (cc & 1) * 4096;
-          if (lane == 0) bulk_wait_read<1>();
+          if (lane == 0) bulk_wait_read<0>();     // the previous store has read the staging tile
           __syncwarp();
           uint8_t* rowp = buf + lane * 128;
 #pragma unroll
@@ -783,7 +795,7 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
     }
     const int max_clusters = cta_cap / 2;
     const int clusters = kp.total_work < max_clusters ? kp.total_work : max_clusters;
-    gemm_tn_pair_kernel<<<2 * clusters, kThreads, kPairSmem, stream>>>(tmA, tmB, tmD, kp);
+    gemm_tn_pair_kernel<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(tmA, tmB, tmD, kp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
   }
