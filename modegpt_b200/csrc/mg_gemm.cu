@@ -262,37 +262,45 @@ __global__ void __launch_bounds__(kThreads, 1)
         // TMA clips at the tensor bounds; in TILES_UPPER chunks that straddle the diagonal are
         // written whole (the strict lower triangle is unspecified by contract).
         uint8_t* buf = epi_smem + (warp - 2) * 4096;
-        if (warp_row0 < p.M) {
-#pragma unroll 1
-          for (int cc = cc_lo; cc < cc_hi; ++cc) {
-            const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
-            if (gc0 >= p.N) break;
-            if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
-            float v[32];
+        // batch this warp's chunks into registers, hand the accumulator back, then stage / store
+        float vv[kChunksPerWarp][32];
+        bool live[kChunksPerWarp];
+#pragma unroll
+        for (int j = 0; j < kChunksPerWarp; ++j) {
+          const int cc = cc_lo + j;
+          const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
+          live[j] = warp_row0 < p.M && gc0 < p.N && !(p.tiles == TILES_UPPER && gc0 + 31 < warp_row0);
+          if (live[j]) {
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                    static_cast<uint32_t>(as * BN + cc * 32);
-            tmem_ld_32x32(taddr, v);
-            tmem_ld_wait();
-            if (lane == 0) bulk_wait_read<0>();  // the previous store has read `buf`
-            __syncwarp();
-            uint8_t* rowp = buf + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2],
-                              p.alpha * v[4 * j + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              const int c0 = (p.tiles == TILES_DIAG) ? cc * 32 : static_cast<int>(gc0);
-              if (p.epi == EPI_STORE) tma_store_2d(&tmD, buf, c0, static_cast<int>(warp_row0));
-              else tma_reduce_add_2d(&tmD, buf, c0, static_cast<int>(warp_row0));
-              bulk_commit();
-            }
+            tmem_ld_32x32(taddr, vv[j]);
           }
         }
+        tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tmem_empty[as]);
+#pragma unroll
+        for (int j = 0; j < kChunksPerWarp; ++j) {
+          if (!live[j]) continue;
+          const int cc = cc_lo + j;
+          const int64_t gc0 = static_cast<int64_t>(wk.nj) * BN + cc * 32;
+          if (lane == 0) bulk_wait_read<0>();  // the previous store has read `buf`
+          __syncwarp();
+          uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(rowp + ((c ^ (lane & 7)) << 4)) =
+                make_float4(p.alpha * vv[j][4 * c], p.alpha * vv[j][4 * c + 1], p.alpha * vv[j][4 * c + 2],
+                            p.alpha * vv[j][4 * c + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = (p.tiles == TILES_DIAG) ? cc * 32 : static_cast<int>(gc0);
+            if (p.epi == EPI_STORE) tma_store_2d(&tmD, buf, c0, static_cast<int>(warp_row0));
+            else tma_reduce_add_2d(&tmD, buf, c0, static_cast<int>(warp_row0));
+            bulk_commit();
+          }
+        }
         continue;
       }
 #pragma unroll 1
@@ -552,36 +560,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int64_t warp_row0 = static_cast<int64_t>(wk.mi) * kPairBM + rank * 128 + q * 32;
-      if (warp_row0 < p.M) {
-#pragma unroll 1
-        for (int cc = chalf * 4; cc < chalf * 4 + 4; ++cc) {
-          const int64_t gc0 = static_cast<int64_t>(wk.nj) * kPairBN + cc * 32;
-          if (gc0 >= p.N) break;
-          if (p.tiles == TILES_UPPER && gc0 + 31 < warp_row0) continue;
-          float v[32];
+      // this warp's four 32-column chunks go to registers in one batch, then the accumulator is
+      // handed back at once: the next-but-one tile's MMAs no longer wait for the staging / TMA
+      // part of the epilogue, only for the TMEM reads
+      float v[4][32];
+      bool live[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = chalf * 4 + j;
+        const int64_t gc0 = static_cast<int64_t>(wk.nj) * kPairBN + cc * 32;
+        live[j] = warp_row0 < p.M && gc0 < p.N && !(p.tiles == TILES_UPPER && gc0 + 31 < warp_row0);
+        if (live[j]) {
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                  static_cast<uint32_t>(as * kPairBN + cc * 32);
-          tmem_ld_32x32(taddr, v);
-          tmem_ld_wait();
-          if (lane == 0) bulk_wait_read<0>();     // the previous store has read the staging tile
-          __syncwarp();
-          uint8_t* rowp = buf + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
-                make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2],
-                            p.alpha * v[4 * j + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.epi == EPI_STORE) tma_store_2d(&tmD, buf, static_cast<int>(gc0), static_cast<int>(warp_row0));
-            else tma_reduce_add_2d(&tmD, buf, static_cast<int>(gc0), static_cast<int>(warp_row0));
-            bulk_commit();
-          }
+          tmem_ld_32x32(taddr, v[j]);
         }
       }
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!live[j]) continue;
+        const int64_t gc0 = static_cast<int64_t>(wk.nj) * kPairBN + (chalf * 4 + j) * 32;
+        if (lane == 0) bulk_wait_read<0>();     // the previous store has read the staging tile
+        __syncwarp();
+        uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(rowp + ((c ^ (lane & 7)) << 4)) =
+              make_float4(p.alpha * v[j][4 * c], p.alpha * v[j][4 * c + 1], p.alpha * v[j][4 * c + 2],
+                          p.alpha * v[j][4 * c + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.epi == EPI_STORE) tma_store_2d(&tmD, buf, static_cast<int>(gc0), static_cast<int>(warp_row0));
+          else tma_reduce_add_2d(&tmD, buf, static_cast<int>(gc0), static_cast<int>(warp_row0));
+          bulk_commit();
+        }
+      }
     }
     if (lane == 0) bulk_wait_all();
   }

@@ -23,6 +23,7 @@ struct Lanes {
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t trsm = nullptr;              // re-recorded by every panel: "block row pj is final"
   cudaEvent_t upd_done[2] = {nullptr, nullptr};   // trailing update of panel pj (parity pj & 1)
+  cudaEvent_t next_done[2] = {nullptr, nullptr};  // block update of the next outer block's rows 2..G
   cudaEvent_t diag_done[2] = {nullptr, nullptr};  // triangular-inverse diagonal block of panel pj
   cudaEvent_t row_done[2] = {nullptr, nullptr};   // triangular-inverse block row pj is final
   cudaEvent_t bulk_done[2] = {nullptr, nullptr};  // look-ahead part of the row's cross product

@@ -542,6 +542,15 @@ DeviceLanes& device_lanes() {
   return per_dev[dev & 63];
 }
 
+int chol_outer_panels() {
+  static const int g = [] {
+    const char* e = std::getenv("MG_CHOL_OUTER");
+    const int v = e ? std::atoi(e) : 4;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  return g;
+}
+
 bool lanes_disabled() {
   static const bool off = [] {
     const char* e = std::getenv("MG_SERIAL");
@@ -572,7 +581,8 @@ LaneScope::LaneScope(cudaStream_t user) {
                           &d.proto.trsm, &d.proto.upd_done[0], &d.proto.upd_done[1],
                           &d.proto.misc[0], &d.proto.misc[1], &d.proto.diag_done[0],
                           &d.proto.diag_done[1], &d.proto.join[3], &d.proto.row_done[0],
-                          &d.proto.row_done[1], &d.proto.bulk_done[0], &d.proto.bulk_done[1]};
+                          &d.proto.row_done[1], &d.proto.bulk_done[0], &d.proto.bulk_done[1],
+                          &d.proto.next_done[0], &d.proto.next_done[1]};
     for (cudaEvent_t* e : evs)
       ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) cudaGetLastError();
@@ -648,6 +658,71 @@ int CholStepper::step(int64_t pj) const {
     t.D = A + (j0 + nb) * ld + (j0 + nb);
     t.tiles = TILES_UPPER;
     MG_TIMED(L.chain, "chol.trailing_syrk", rc = gemm_tn_launch(t, L.chain));
+    return rc;
+  }
+  const int G = chol_outer_panels();
+  if (G > 1) {
+    // Two-level blocking: panels are grouped into outer blocks of G.  Inside a block a panel only
+    // updates the block's remaining rows (K = 128, small); the rows below the block get ONE update
+    // per block with K = G * 128 — a quarter of the read-modify-write passes over the trailing
+    // matrix and four times the MMA work per epilogue (the K = 128 update is paced by its L2
+    // reduce-adds: 44 % tensor pipe in ncu).  Look-ahead: of that block update only the next
+    // block's first row sits on the chain; its other rows and everything below run on the upd lane.
+    const int64_t q = pj % G, ob = pj / G;
+    const int64_t o0 = ob * G * kNB;
+    const int64_t o_end = (o0 + G * kNB < n) ? o0 + G * kNB : n;
+    const int64_t in_block = o_end - (j0 + nb);          // rows of this block below panel pj
+    if (in_block > 0) {
+      // (ordered adds) the previous block's update of these rows comes from the upd lane
+      if (q == 0 && ob >= 1) L.wait(L.chain, L.next_done[(ob - 1) & 1]);
+      t.A = u12;
+      t.B = u12;
+      t.M = in_block;
+      t.N = rest;
+      t.D = A + (j0 + nb) * ld + (j0 + nb);
+      t.tiles = TILES_FULL;   // below-diagonal parts of these rows are scratch
+      MG_TIMED(L.chain, "chol.row_update", rc = gemm_tn_launch(t, L.chain));
+      return rc;
+    }
+    // panel pj closes its block: rows >= o_end get the whole block at once (K = o_end - o0)
+    const __nv_bfloat16* blk = ws.u_planes + o0 * np;    // block rows o0 .. o_end of U
+    t.K = o_end - o0;
+    const int64_t first = rest < kNB ? rest : kNB;
+    const int64_t next_rows = rest < G * kNB ? rest : G * kNB;
+    L.wait(L.upd, L.trsm);
+    if (next_rows > first) {          // rows 2..G of the next block
+      GemmArgs r = t;
+      r.A = blk + (o_end + first);
+      r.B = blk + (o_end + first);
+      r.M = next_rows - first;
+      r.N = rest - first;
+      r.D = A + (o_end + first) * ld + (o_end + first);
+      r.tiles = TILES_FULL;
+      r.max_ctas = L.bulk_cta_cap();
+      MG_TIMED(L.upd, "chol.block_update_next", rc = gemm_tn_launch(r, L.upd));
+      if (rc) return rc;
+    }
+    L.record(L.next_done[ob & 1], L.upd);
+    if (rest > next_rows) {           // everything below the next block
+      GemmArgs r = t;
+      r.A = r.B = blk + (o_end + next_rows);
+      r.M = r.N = rest - next_rows;
+      r.D = A + (o_end + next_rows) * ld + (o_end + next_rows);
+      r.tiles = TILES_UPPER;
+      r.max_ctas = L.bulk_cta_cap();
+      MG_TIMED(L.upd, "chol.trailing_syrk", rc = gemm_tn_launch(r, L.upd));
+      if (rc) return rc;
+    }
+    L.record(L.upd_done[ob & 1], L.upd);
+    // chain: the next block's first row (it also received the previous block's trailing update)
+    if (ob >= 1) L.wait(L.chain, L.upd_done[(ob - 1) & 1]);
+    t.A = blk + o_end;
+    t.B = blk + o_end;
+    t.M = first;
+    t.N = rest;
+    t.D = A + o_end * ld + o_end;
+    t.tiles = TILES_FULL;
+    MG_TIMED(L.chain, "chol.block_update_first", rc = gemm_tn_launch(t, L.chain));
     return rc;
   }
   const int64_t m1 = rest < kNB ? rest : kNB;

@@ -139,8 +139,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  // default semantics (release at CTA scope), as the accumulator hand-off only has to order this
+  // thread's own tcgen05.ld (fenced by tcgen05.fence::before_thread_sync) before the arrive; the
+  // .release.cluster form compiled to MEMBAR + ERRBAR and held every tile for all outstanding
+  // stores — 30 % of the warp samples of a short-K update in ncu
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's smem whose completion bytes are credited to a barrier that may live in
 // the peer CTA of the pair (cluster address).

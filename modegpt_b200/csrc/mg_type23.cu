@@ -83,7 +83,7 @@ constexpr int kMaxHd = 128;
 
 struct EigSmem {
   double* g;     // [hd][hd+1]   matrix being diagonalised (fp64)
-  float* v;      // [hd][hd+1]   accumulated eigenvectors (fp32)
+  float* v;      // [hd][hd+4]   accumulated eigenvectors (fp32); transposed while the sweeps run
   double* cs;    // [hd]         (c, s) per pair
   int* pq;       // [hd]         (p, q) per pair
   double* lam;   // [hd]
@@ -102,7 +102,7 @@ __device__ __forceinline__ EigSmem carve_eig(uint8_t* base, int hd) {
   s.red = reinterpret_cast<double*>(base);
   base += sizeof(double) * 64;
   s.v = reinterpret_cast<float*>(base);
-  base += sizeof(float) * hd * (hd + 1);
+  base += sizeof(float) * hd * (hd + 4);
   s.pq = reinterpret_cast<int*>(base);
   base += sizeof(int) * hd;
   s.perm = reinterpret_cast<int*>(base);
@@ -111,7 +111,7 @@ __device__ __forceinline__ EigSmem carve_eig(uint8_t* base, int hd) {
 
 size_t eig_smem_bytes(int hd) {
   return sizeof(double) * hd * (hd + 1) + sizeof(double) * (2 * hd + 64) +
-         sizeof(float) * hd * (hd + 1) + sizeof(int) * 2 * hd + 64;
+         sizeof(float) * hd * (hd + 4) + sizeof(int) * 2 * hd + 64;
 }
 
 __device__ double block_sum(double x, double* red) {
@@ -132,20 +132,38 @@ __device__ double block_sum(double x, double* red) {
 // columns of v[] the matching eigenvectors (v is rewritten in sorted order via perm).
 __device__ void jacobi_eig(EigSmem& s, int hd) {
   const int t = threadIdx.x, nt = blockDim.x;
-  const int ld = hd + 1;
+  const int ld = hd + 1, ldv = hd + 4;
   const int half = hd / 2, m = hd - 1;
+  // the (k <= l) pair blocks this thread owns in every step (the assignment does not depend on
+  // the step: only the index pairs behind k and l move)
+  constexpr int kMaxBlocksPerThread = 3;   // 64 * 65 / 2 = 2080 blocks over 1024 threads
+  int my_blocks[kMaxBlocksPerThread];
+#pragma unroll
+  for (int b = 0; b < kMaxBlocksPerThread; ++b) {
+    const int e = t + b * nt;
+    my_blocks[b] = -1;
+    if (e < half * (half + 1) / 2) {
+      int l = static_cast<int>((sqrtf(8.f * static_cast<float>(e) + 1.f) - 1.f) * 0.5f);
+      while (l * (l + 1) / 2 > e) --l;
+      while ((l + 1) * (l + 2) / 2 <= e) ++l;
+      my_blocks[b] = ((e - l * (l + 1) / 2) << 8) | l;
+    }
+  }
+  // V is kept TRANSPOSED during the sweeps (vt[col][row], rows 16-byte aligned): rotating columns
+  // p, q of V is then a rotation of two contiguous rows, four components per 16-byte access
   for (int e = t; e < hd * hd; e += nt) {
     const int i = e / hd, k = e - i * hd;
-    s.v[i * ld + k] = (i == k) ? 1.f : 0.f;
+    s.v[i * ldv + k] = (i == k) ? 1.f : 0.f;
   }
   __syncthreads();
   for (int sweep = 0; sweep < 30; ++sweep) {
     double off = 0.0, dg = 0.0;
     for (int e = t; e < hd * hd; e += nt) {
       const int i = e / hd, k = e - i * hd;
+      if (i > k) continue;                     // the strict lower triangle is stale
       const double x = s.g[i * ld + k];
       if (i == k) dg += x * x;
-      else off += x * x;
+      else off += 2.0 * x * x;
     }
     off = block_sum(off, s.red);
     dg = block_sum(dg, s.red);
@@ -179,37 +197,60 @@ __device__ void jacobi_eig(EigSmem& s, int hd) {
         s.pq[2 * t + 1] = q;
       }
       __syncthreads();
-      // G <- J^T G J in one pass: the 64 x 64 pair blocks {p_k,q_k} x {p_l,q_l} are disjoint, so
-      // each 2 x 2 block is read, rotated on both sides and written back by one thread
-      for (int e = t; e < half * half; e += nt) {
-        const int k = e / half, l = e - k * half;
+      // G <- J^T G J in one pass over the pair blocks {p_k,q_k} x {p_l,q_l} with k <= l: the
+      // blocks are disjoint, G stays symmetric, and only its upper triangle (row <= column) is
+      // stored and touched — each 2 x 2 block is read, rotated on both sides and written back
+      // by one thread (block (l, k) is the mirror image and is never formed)
+#pragma unroll
+      for (int b = 0; b < kMaxBlocksPerThread; ++b) {
+        const int kl = my_blocks[b];
+        if (kl < 0) break;
+        const int k = kl >> 8, l = kl & 255;
         const int pk = s.pq[2 * k], qk = s.pq[2 * k + 1];
         const int pl = s.pq[2 * l], ql = s.pq[2 * l + 1];
         const double ck = s.cs[2 * k], sk = s.cs[2 * k + 1];
         const double cl = s.cs[2 * l], sl = s.cs[2 * l + 1];
-        const double gpp = s.g[pk * ld + pl], gpq = s.g[pk * ld + ql];
-        const double gqp = s.g[qk * ld + pl], gqq = s.g[qk * ld + ql];
+        double* e_pp = s.g + (pk <= pl ? pk * ld + pl : pl * ld + pk);
+        double* e_pq = s.g + (pk <= ql ? pk * ld + ql : ql * ld + pk);
+        double* e_qp = s.g + (qk <= pl ? qk * ld + pl : pl * ld + qk);
+        double* e_qq = s.g + (qk <= ql ? qk * ld + ql : ql * ld + qk);
+        const double gpp = *e_pp, gpq = *e_pq, gqp = *e_qp, gqq = *e_qq;
         // right rotation (columns pl, ql)
         const double a_pp = cl * gpp - sl * gpq, a_pq = sl * gpp + cl * gpq;
         const double a_qp = cl * gqp - sl * gqq, a_qq = sl * gqp + cl * gqq;
         // left rotation (rows pk, qk)
-        s.g[pk * ld + pl] = ck * a_pp - sk * a_qp;
-        s.g[pk * ld + ql] = ck * a_pq - sk * a_qq;
-        s.g[qk * ld + pl] = sk * a_pp + ck * a_qp;
-        s.g[qk * ld + ql] = sk * a_pq + ck * a_qq;
+        *e_pp = ck * a_pp - sk * a_qp;
+        *e_pq = ck * a_pq - sk * a_qq;
+        *e_qp = sk * a_pp + ck * a_qp;
+        *e_qq = sk * a_pq + ck * a_qq;
       }
-      // V <- V J
-      for (int e = t; e < hd * half; e += nt) {
-        const int k = e / hd, i = e - k * hd;
+      // V <- V J  (rows p, q of the transposed store)
+      const int quads = hd / 4;
+      for (int e = t; e < quads * half; e += nt) {
+        const int k = e / quads, i4 = e - k * quads;
         const int p = s.pq[2 * k], q = s.pq[2 * k + 1];
         const double c = s.cs[2 * k], sn = s.cs[2 * k + 1];
-        const float vp = s.v[i * ld + p], vq = s.v[i * ld + q];
-        s.v[i * ld + p] = static_cast<float>(c * vp - sn * vq);
-        s.v[i * ld + q] = static_cast<float>(sn * vp + c * vq);
+        float4* rp = reinterpret_cast<float4*>(s.v + p * ldv) + i4;
+        float4* rq = reinterpret_cast<float4*>(s.v + q * ldv) + i4;
+        const float4 vp = *rp, vq = *rq;
+        *rp = make_float4(static_cast<float>(c * vp.x - sn * vq.x), static_cast<float>(c * vp.y - sn * vq.y),
+                          static_cast<float>(c * vp.z - sn * vq.z), static_cast<float>(c * vp.w - sn * vq.w));
+        *rq = make_float4(static_cast<float>(sn * vp.x + c * vq.x), static_cast<float>(sn * vp.y + c * vq.y),
+                          static_cast<float>(sn * vp.z + c * vq.z), static_cast<float>(sn * vp.w + c * vq.w));
       }
       __syncthreads();
     }
   }
+  // back to v[row][col] for the callers
+  for (int e = t; e < hd * hd; e += nt) {
+    const int i = e / hd, k = e - i * hd;
+    if (i < k) {
+      const float x = s.v[i * ldv + k];
+      s.v[i * ldv + k] = s.v[k * ldv + i];
+      s.v[k * ldv + i] = x;
+    }
+  }
+  __syncthreads();
   // sort descending (rank by counting), stable on index
   if (t < hd) s.lam[t] = s.g[t * ld + t];
   __syncthreads();
@@ -231,7 +272,7 @@ __global__ void __launch_bounds__(1024, 1)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EigSmem s = carve_eig(smem_raw, hd);
   const int t = threadIdx.x, nt = blockDim.x;
-  const int ld = hd + 1;
+  const int ld = hd + 1, ldv = hd + 4;
   const int h = blockIdx.x;
   const float* g1 = G1 + static_cast<int64_t>(h) * hd * hd;
   float* rv = Rv + static_cast<int64_t>(h) * hd * r;
@@ -250,7 +291,7 @@ __global__ void __launch_bounds__(1024, 1)
       const int i = e / r, a = e - i * r;
       const int col = s.perm[a];
       const double sv = sqrt(fmax(s.lam[col], 0.0));
-      const double v = s.v[i * ld + col];
+      const double v = s.v[i * ldv + col];
       rv[e] = static_cast<float>(v / fmax(sv, 1e-30));
       ro[e] = static_cast<float>(v * sv);
     }
@@ -265,13 +306,13 @@ __global__ void __launch_bounds__(1024, 1)
   if (t < hd) sval[t] = sqrt(fmax(s.lam[s.perm[t]], 0.0));
   for (int e = t; e < hd * hd; e += nt) {
     const int i = e / hd, a = e - i * hd;
-    vg[e] = s.v[i * ld + s.perm[a]];
+    vg[e] = s.v[i * ldv + s.perm[a]];
   }
   __syncthreads();
   // D = V S in shared memory (overwrites v, sorted order)
   for (int e = t; e < hd * hd; e += nt) {
     const int i = e / hd, a = e - i * hd;
-    s.v[i * ld + a] = static_cast<float>(static_cast<double>(vg[e]) * sval[a]);
+    s.v[i * ldv + a] = static_cast<float>(static_cast<double>(vg[e]) * sval[a]);
   }
   __syncthreads();
   // T = G2 D
@@ -280,7 +321,7 @@ __global__ void __launch_bounds__(1024, 1)
     double acc = 0.0;
     for (int k = 0; k < hd; ++k)
       acc += 0.5 * (static_cast<double>(g2[i * hd + k]) + static_cast<double>(g2[k * hd + i])) *
-             static_cast<double>(s.v[k * ld + a]);
+             static_cast<double>(s.v[k * ldv + a]);
     tg[e] = static_cast<float>(acc);
   }
   __syncthreads();
@@ -289,7 +330,7 @@ __global__ void __launch_bounds__(1024, 1)
     const int a = e / hd, b = e - a * hd;
     double acc = 0.0;
     for (int k = 0; k < hd; ++k)
-      acc += static_cast<double>(s.v[k * ld + a]) * static_cast<double>(tg[k * hd + b]);
+      acc += static_cast<double>(s.v[k * ldv + a]) * static_cast<double>(tg[k * hd + b]);
     s.g[a * ld + b] = acc;
   }
   __syncthreads();
@@ -313,7 +354,7 @@ __global__ void __launch_bounds__(1024, 1)
     double av = 0.0, ao = 0.0;
     for (int k = 0; k < hd; ++k) {
       const double v = vg[i * hd + k];
-      const double up = s.v[k * ld + col];
+      const double up = s.v[k * ldv + col];
       const double sv = s_keep[k];
       av += v / fmax(sv, 1e-30) * up;
       ao += v * sv * up;

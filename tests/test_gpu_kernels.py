@@ -359,3 +359,29 @@ def test_type1_repeated_calls_agree(ops):
         again = ops.ridge_scores(c, 1e-3)
         assert rel(again.cpu().numpy(), first.cpu().numpy()) < 1e-6
         assert torch.equal(ops.select_k(again, 800), idx)
+
+
+def test_layer_writer_roundtrip_from_device(tmp_path):
+    """handoff.LayerWriter on CUDA tensors: transposed views, biases, int64 masks and tensors larger
+    than one 64 MB staging slice come back bit-identical through torch.load."""
+    from modegpt_b200.handoff import LayerWriter
+
+    g = torch.Generator().manual_seed(9)
+    w = LayerWriter(n_threads=2, max_in_flight=3)
+    expect = {}
+    for i in range(5):
+        big = torch.randn(4096 + i, 9000, generator=g).bfloat16().to(DEV)          # ~74 MB: two slices
+        d = {"up": big, "down": torch.randn(64, 300 + i, generator=g).bfloat16().to(DEV).T,
+             "bias": torch.randn(300 + i, generator=g).bfloat16().to(DEV),
+             "mask": torch.arange(4 * (10 + i), device=DEV).view(4, -1)}
+        path = tmp_path / f"layer_{i}_mlp"
+        w.submit(str(path), d)
+        expect[path] = {k: v.cpu() for k, v in d.items()}
+        del big, d
+    w.flush()
+    for path, d in expect.items():
+        got = torch.load(path)
+        assert set(got) == set(d)
+        for k in d:
+            assert got[k].dtype == d[k].dtype and got[k].shape == d[k].shape and torch.equal(got[k], d[k])
+    w.close()
