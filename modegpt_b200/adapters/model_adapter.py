@@ -380,7 +380,7 @@ class ModelAdapter(ABC):
             return
         from ..handoff import LayerWriter
 
-        self._writer = LayerWriter()
+        self._writer = LayerWriter(device=next(self.model.parameters()).device)
 
     def flush_saves(self) -> None:
         """Block until every submitted layer file is on disk (raises if a write failed)."""

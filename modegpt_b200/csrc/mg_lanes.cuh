@@ -18,11 +18,14 @@
 namespace mg {
 
 struct Lanes {
-  cudaStream_t chain = nullptr, upd = nullptr, tri = nullptr, tri2 = nullptr;
+  cudaStream_t chain = nullptr, chain2 = nullptr, upd = nullptr, tri = nullptr, tri2 = nullptr;
   cudaStream_t user = nullptr;
-  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t trsm = nullptr;              // re-recorded by every panel: "block row pj is final"
   cudaEvent_t upd_done[2] = {nullptr, nullptr};   // trailing update of panel pj (parity pj & 1)
+  cudaEvent_t potrf = nullptr;                      // diagonal block of panel pj factored
+  cudaEvent_t first[2] = {nullptr, nullptr};       // first 256 columns of block row pj solved (chain)
+  cudaEvent_t row_rest[2] = {nullptr, nullptr};    // chain2's row updates of panel pj landed
   cudaEvent_t next_done[2] = {nullptr, nullptr};  // block update of the next outer block's rows 2..G
   cudaEvent_t diag_done[2] = {nullptr, nullptr};  // triangular-inverse diagonal block of panel pj
   cudaEvent_t row_done[2] = {nullptr, nullptr};   // triangular-inverse block row pj is final

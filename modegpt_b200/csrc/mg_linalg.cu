@@ -32,16 +32,13 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16
   lo = __float2bfloat16_rn(r2);
 }
 
-// 1/sqrt(x) for x in the float range: single-precision seed + two Newton steps (full double
-// accuracy, a third of the latency of the library routine; the pivot loops sit on it).
+// 1/sqrt(x) for x in the float range: single-precision seed y0 (relative error e ~ 2^-22) and one
+// third-order correction y0 (1 + e/2 + 3 e^2 / 8), e = 1 - x y0^2 — the neglected term is
+// 5 e^3 / 16 < 1e-19.  Four dependent fp64 operations; the pivot loops sit on this latency.
 __device__ __forceinline__ double rsqrt_pos(double x) {
-  double y = static_cast<double>(rsqrtf(static_cast<float>(x)));
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double e = fma(-x * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
-  }
-  return y;
+  const double y0 = static_cast<double>(rsqrtf(static_cast<float>(x)));
+  const double e = fma(-x * y0, y0, 1.0);
+  return fma(y0 * e, fma(0.375, e, 0.5), y0);
 }
 
 // D (8 x 8, fp64) += A (8 x 4, row) * B (4 x 8, col) on the FP64 tensor cores; per-thread fragments:
@@ -560,10 +557,18 @@ bool lanes_disabled() {
 }
 }  // namespace
 
-int Lanes::bulk_cta_cap() const { return serial ? 0 : device_sm_count() - 4; }
+int Lanes::bulk_cta_cap() const {
+  static const int reserve = [] {
+    const char* e = std::getenv("MG_BULK_RESERVE_SMS");   // SMs kept free of persistent bulk CTAs
+    const int v = e ? std::atoi(e) : 48;   // measured: Nystrom 12.8 -> 11.7 ms from 4 -> 52, ridge flat
+    return v < 0 ? 0 : v;
+  }();
+  const int cap = device_sm_count() - reserve;
+  return serial ? 0 : (cap < 16 ? 16 : cap);
+}
 
 LaneScope::LaneScope(cudaStream_t user) {
-  lanes_.user = lanes_.chain = lanes_.upd = lanes_.tri = lanes_.tri2 = user;
+  lanes_.user = lanes_.chain = lanes_.chain2 = lanes_.upd = lanes_.tri = lanes_.tri2 = user;
   lanes_.serial = true;
   if (lanes_disabled()) return;
   DeviceLanes& d = device_lanes();
@@ -574,6 +579,7 @@ LaneScope::LaneScope(cudaStream_t user) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least urgent, hi = most urgent
     bool ok = cudaStreamCreateWithPriority(&d.proto.chain, cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&d.proto.chain2, cudaStreamNonBlocking, hi) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&d.proto.upd, cudaStreamNonBlocking, lo) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&d.proto.tri, cudaStreamNonBlocking, lo) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&d.proto.tri2, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -582,7 +588,8 @@ LaneScope::LaneScope(cudaStream_t user) {
                           &d.proto.misc[0], &d.proto.misc[1], &d.proto.diag_done[0],
                           &d.proto.diag_done[1], &d.proto.join[3], &d.proto.row_done[0],
                           &d.proto.row_done[1], &d.proto.bulk_done[0], &d.proto.bulk_done[1],
-                          &d.proto.next_done[0], &d.proto.next_done[1]};
+                          &d.proto.next_done[0], &d.proto.next_done[1], &d.proto.join[4], &d.proto.potrf,
+                          &d.proto.first[0], &d.proto.first[1], &d.proto.row_rest[0], &d.proto.row_rest[1]};
     for (cudaEvent_t* e : evs)
       ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) cudaGetLastError();
@@ -597,12 +604,13 @@ LaneScope::LaneScope(cudaStream_t user) {
   cudaStreamWaitEvent(lanes_.upd, lanes_.fork, 0);
   cudaStreamWaitEvent(lanes_.tri, lanes_.fork, 0);
   cudaStreamWaitEvent(lanes_.tri2, lanes_.fork, 0);
+  cudaStreamWaitEvent(lanes_.chain2, lanes_.fork, 0);
 }
 
 LaneScope::~LaneScope() {
   if (!lanes_.serial) {
-    cudaStream_t ls[4] = {lanes_.chain, lanes_.upd, lanes_.tri, lanes_.tri2};
-    for (int i = 0; i < 4; ++i) {
+    cudaStream_t ls[5] = {lanes_.chain, lanes_.upd, lanes_.tri, lanes_.tri2, lanes_.chain2};
+    for (int i = 0; i < 5; ++i) {
       cudaEventRecord(lanes_.join[i], ls[i]);
       cudaStreamWaitEvent(lanes_.user, lanes_.join[i], 0);
     }
@@ -613,7 +621,7 @@ LaneScope::~LaneScope() {
 // ---------------------------------------------------------------------------------------------
 // blocked Cholesky
 // ---------------------------------------------------------------------------------------------
-int CholStepper::step(int64_t pj) const {
+int CholStepper::step_panelwise(int64_t pj) const {
   const Lanes& L = *lanes;
   const int64_t np = ws.n_pad;
   const int64_t pstride = np * np;
@@ -660,71 +668,6 @@ int CholStepper::step(int64_t pj) const {
     MG_TIMED(L.chain, "chol.trailing_syrk", rc = gemm_tn_launch(t, L.chain));
     return rc;
   }
-  const int G = chol_outer_panels();
-  if (G > 1) {
-    // Two-level blocking: panels are grouped into outer blocks of G.  Inside a block a panel only
-    // updates the block's remaining rows (K = 128, small); the rows below the block get ONE update
-    // per block with K = G * 128 — a quarter of the read-modify-write passes over the trailing
-    // matrix and four times the MMA work per epilogue (the K = 128 update is paced by its L2
-    // reduce-adds: 44 % tensor pipe in ncu).  Look-ahead: of that block update only the next
-    // block's first row sits on the chain; its other rows and everything below run on the upd lane.
-    const int64_t q = pj % G, ob = pj / G;
-    const int64_t o0 = ob * G * kNB;
-    const int64_t o_end = (o0 + G * kNB < n) ? o0 + G * kNB : n;
-    const int64_t in_block = o_end - (j0 + nb);          // rows of this block below panel pj
-    if (in_block > 0) {
-      // (ordered adds) the previous block's update of these rows comes from the upd lane
-      if (q == 0 && ob >= 1) L.wait(L.chain, L.next_done[(ob - 1) & 1]);
-      t.A = u12;
-      t.B = u12;
-      t.M = in_block;
-      t.N = rest;
-      t.D = A + (j0 + nb) * ld + (j0 + nb);
-      t.tiles = TILES_FULL;   // below-diagonal parts of these rows are scratch
-      MG_TIMED(L.chain, "chol.row_update", rc = gemm_tn_launch(t, L.chain));
-      return rc;
-    }
-    // panel pj closes its block: rows >= o_end get the whole block at once (K = o_end - o0)
-    const __nv_bfloat16* blk = ws.u_planes + o0 * np;    // block rows o0 .. o_end of U
-    t.K = o_end - o0;
-    const int64_t first = rest < kNB ? rest : kNB;
-    const int64_t next_rows = rest < G * kNB ? rest : G * kNB;
-    L.wait(L.upd, L.trsm);
-    if (next_rows > first) {          // rows 2..G of the next block
-      GemmArgs r = t;
-      r.A = blk + (o_end + first);
-      r.B = blk + (o_end + first);
-      r.M = next_rows - first;
-      r.N = rest - first;
-      r.D = A + (o_end + first) * ld + (o_end + first);
-      r.tiles = TILES_FULL;
-      r.max_ctas = L.bulk_cta_cap();
-      MG_TIMED(L.upd, "chol.block_update_next", rc = gemm_tn_launch(r, L.upd));
-      if (rc) return rc;
-    }
-    L.record(L.next_done[ob & 1], L.upd);
-    if (rest > next_rows) {           // everything below the next block
-      GemmArgs r = t;
-      r.A = r.B = blk + (o_end + next_rows);
-      r.M = r.N = rest - next_rows;
-      r.D = A + (o_end + next_rows) * ld + (o_end + next_rows);
-      r.tiles = TILES_UPPER;
-      r.max_ctas = L.bulk_cta_cap();
-      MG_TIMED(L.upd, "chol.trailing_syrk", rc = gemm_tn_launch(r, L.upd));
-      if (rc) return rc;
-    }
-    L.record(L.upd_done[ob & 1], L.upd);
-    // chain: the next block's first row (it also received the previous block's trailing update)
-    if (ob >= 1) L.wait(L.chain, L.upd_done[(ob - 1) & 1]);
-    t.A = blk + o_end;
-    t.B = blk + o_end;
-    t.M = first;
-    t.N = rest;
-    t.D = A + o_end * ld + o_end;
-    t.tiles = TILES_FULL;
-    MG_TIMED(L.chain, "chol.block_update_first", rc = gemm_tn_launch(t, L.chain));
-    return rc;
-  }
   const int64_t m1 = rest < kNB ? rest : kNB;
   const int64_t rest2 = rest - m1;
   if (rest2 > 0) {
@@ -749,6 +692,173 @@ int CholStepper::step(int64_t pj) const {
   t.tiles = TILES_FULL;   // 128 x rest: the strict lower part of its diagonal block is scratch
   MG_TIMED(L.chain, "chol.row_update", rc = gemm_tn_launch(t, L.chain));
   return rc;
+}
+
+// Two-level blocking: panels are grouped into outer blocks of G (MG_CHOL_OUTER, default 4).  Inside
+// a block a panel only updates the block's remaining rows (K = 128, small); the rows below the
+// block get ONE update per block with K = G * 128 — a quarter of the read-modify-write passes over
+// the trailing matrix and four times the MMA work per epilogue (the K = 128 trailing update is
+// paced by its L2 reduce-adds: 44 % tensor pipe in ncu, 75 % at K = 512).
+//
+// Split-chain step (lanes on, outer blocks of G > 1 panels).  What the NEXT panel's potrf128 needs
+// from panel pj is tiny: the first 384 solved columns of block row pj and the update of one
+// 128 x 384 tile.  Only those stay on the chain lane; the rest of the block row's solve and of the
+// row updates run on chain2, concurrently with the next potrf128:
+//   chain : potrf128(pj) -> trsm128(first 384 cols) -> tile update (next block row x 384 cols)
+//   chain2: trsm128(remaining cols) -> [block row pj final: records lanes.trsm] -> remaining row
+//           updates of the outer block (K = 128)            [records row_rest[pj & 1]]
+//   upd   : at the end of an outer block, the K = G*128 update of everything below it
+// Ordered adds: chain waits for chain2's row updates of panel pj-1 before its own tile update
+// (they overlap on block row pj+1), both wait for the upd lane's block update of their rows.
+int CholStepper::step(int64_t pj) const {
+  const Lanes& L = *lanes;
+  const int G = chol_outer_panels();
+  if (L.serial || G <= 1) return step_panelwise(pj);
+  const int64_t np = ws.n_pad;
+  const int64_t pstride = np * np;
+  const int64_t j0 = pj * kNB;
+  const int nb = static_cast<int>(n - j0 < kNB ? n - j0 : kNB);
+  float* tf = ws.t_fwd + pj * kTBlock;
+  float* tb = ws.t_bwd ? ws.t_bwd + pj * kTBlock : nullptr;
+  int rc;
+  MG_TIMED(L.chain, "chol.potrf128", rc = potrf128(A, ld, j0, nb, tf, tb, info, L.chain));
+  if (rc) return rc;
+  const int64_t rest = n - j0 - nb;
+  if (rest <= 0) {
+    L.record(L.trsm, L.chain);
+    return 0;
+  }
+  L.record(L.potrf, L.chain);
+  const int64_t c0 = j0 + nb;                       // first column / row below the panel
+  float* a12 = A + j0 * ld + c0;
+  __nv_bfloat16* u12 = ws.u_planes + j0 * np + c0;
+  __nv_bfloat16* l21 = ws.l_planes ? ws.l_planes + c0 * np + j0 : nullptr;
+  // the chain's update tile spans the next diagonal block plus the 256 columns the next panel
+  // solves first; its operands must all come from the chain's own solve, so that solve covers
+  // the same 384 columns
+  const int64_t tw = rest < 384 ? rest : 384;
+  const int64_t sw = tw;
+  const int64_t fr = rest < kNB ? rest : kNB;       // rows of the next block row
+  MG_TIMED(L.chain, "chol.trsm128_first",
+           rc = trsm128(tf, false, nb, a12, ld, sw, 1.f, a12, ld, u12, np, pstride, l21, np, pstride,
+                        nullptr, L.chain));
+  if (rc) return rc;
+  L.record(L.first[pj & 1], L.chain);
+  L.wait(L.chain2, L.potrf);
+  if (rest > sw) {
+    MG_TIMED(L.chain2, "chol.trsm128_rest",
+             rc = trsm128(tf, false, nb, a12 + sw, ld, rest - sw, 1.f, a12 + sw, ld, u12 + sw, np, pstride,
+                          l21 ? l21 + sw * np : nullptr, np, pstride, nullptr, L.chain2));
+    if (rc) return rc;
+  }
+  L.wait(L.chain2, L.first[pj & 1]);
+  L.record(L.trsm, L.chain2);                       // block row pj of U is final
+
+  GemmArgs t{};
+  t.lda = t.ldb = np;
+  t.a_plane_stride = t.b_plane_stride = pstride;
+  t.a_planes = t.b_planes = kPlanes;
+  set_pairs6(t);
+  t.ldd = ld;
+  t.alpha = -1.f;
+  t.epi = EPI_ADD;
+  t.ksplit = 1;
+  t.tiles = TILES_FULL;                              // below-diagonal parts of a block row are scratch
+
+  const int64_t q = pj % G, ob = pj / G;
+  const int64_t o0 = ob * G * kNB;
+  const int64_t o_end = (o0 + G * kNB < n) ? o0 + G * kNB : n;
+  const int64_t in_block = o_end - c0;               // rows of this outer block below panel pj
+  float* d0 = A + c0 * ld + c0;
+  if (in_block > 0) {
+    // ---- inside the block: K = 128 updates of the block's remaining rows
+    t.K = nb;
+    if (q == 0 && ob >= 1) {
+      L.wait(L.chain, L.next_done[(ob - 1) & 1]);
+      L.wait(L.chain2, L.next_done[(ob - 1) & 1]);
+    }
+    if (pj >= 1) L.wait(L.chain, L.row_rest[(pj - 1) & 1]);
+    t.A = u12;
+    t.B = u12;
+    t.M = fr;
+    t.N = tw;
+    t.D = d0;
+    MG_TIMED(L.chain, "chol.tile_update", rc = gemm_tn_launch(t, L.chain));
+    if (rc) return rc;
+    if (rest > tw) {                                  // next block row, columns right of the tile
+      GemmArgs r = t;
+      r.B = u12 + tw;
+      r.N = rest - tw;
+      r.D = d0 + tw;
+      MG_TIMED(L.chain2, "chol.row_update", rc = gemm_tn_launch(r, L.chain2));
+      if (rc) return rc;
+    }
+    if (in_block > fr) {                              // the block's rows below the next block row
+      GemmArgs r = t;
+      r.A = u12 + fr;
+      r.B = u12 + fr;
+      r.M = in_block - fr;
+      r.N = rest - fr;
+      r.D = d0 + fr * ld + fr;
+      MG_TIMED(L.chain2, "chol.row_update", rc = gemm_tn_launch(r, L.chain2));
+      if (rc) return rc;
+    }
+    L.record(L.row_rest[pj & 1], L.chain2);
+    return 0;
+  }
+  // ---- panel pj closes its block: rows >= o_end (= c0) get the whole block at once
+  const __nv_bfloat16* blk = ws.u_planes + o0 * np;  // block rows o0 .. o_end of U
+  t.K = o_end - o0;
+  const int64_t next_rows = rest < G * kNB ? rest : G * kNB;
+  L.wait(L.upd, L.trsm);
+  if (next_rows > fr) {                               // rows 2..G of the next block
+    GemmArgs r = t;
+    r.A = blk + (c0 + fr);
+    r.B = blk + (c0 + fr);
+    r.M = next_rows - fr;
+    r.N = rest - fr;
+    r.D = d0 + fr * ld + fr;
+    r.max_ctas = L.bulk_cta_cap();
+    MG_TIMED(L.upd, "chol.block_update_next", rc = gemm_tn_launch(r, L.upd));
+    if (rc) return rc;
+  }
+  L.record(L.next_done[ob & 1], L.upd);
+  if (rest > next_rows) {                             // everything below the next block
+    GemmArgs r = t;
+    r.A = r.B = blk + (c0 + next_rows);
+    r.M = r.N = rest - next_rows;
+    r.D = d0 + next_rows * ld + next_rows;
+    r.tiles = TILES_UPPER;
+    r.max_ctas = L.bulk_cta_cap();
+    MG_TIMED(L.upd, "chol.trailing_syrk", rc = gemm_tn_launch(r, L.upd));
+    if (rc) return rc;
+  }
+  L.record(L.upd_done[ob & 1], L.upd);
+  // the next block's first row: tile on the chain, the rest of the row on chain2.  Both read every
+  // block row of this outer block: the earlier ones were finished by chain2 (row_rest of pj-1
+  // follows their solves in stream order), this one by the solves above.
+  if (ob >= 1) {
+    L.wait(L.chain, L.upd_done[(ob - 1) & 1]);
+    L.wait(L.chain2, L.upd_done[(ob - 1) & 1]);
+  }
+  if (pj >= 1) L.wait(L.chain, L.row_rest[(pj - 1) & 1]);
+  t.A = blk + c0;
+  t.B = blk + c0;
+  t.M = fr;
+  t.N = tw;
+  t.D = d0;
+  MG_TIMED(L.chain, "chol.block_tile_update", rc = gemm_tn_launch(t, L.chain));
+  if (rc) return rc;
+  if (rest > tw) {
+    GemmArgs r = t;
+    r.B = blk + c0 + tw;
+    r.N = rest - tw;
+    r.D = d0 + tw;
+    MG_TIMED(L.chain2, "chol.block_update_first", rc = gemm_tn_launch(r, L.chain2));
+    if (rc) return rc;
+  }
+  L.record(L.row_rest[pj & 1], L.chain2);
+  return 0;
 }
 
 int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int* info,

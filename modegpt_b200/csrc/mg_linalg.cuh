@@ -72,6 +72,7 @@ struct CholStepper {
   const Lanes* lanes;
   int64_t panels() const { return (n + kNB - 1) / kNB; }
   int step(int64_t pj) const;
+  int step_panelwise(int64_t pj) const;   // one stream / MG_CHOL_OUTER=1: panel-wise right-looking
 };
 
 int cholesky_upper(float* A, int64_t n, int64_t ld, const CholWorkspace& ws, int* info,

@@ -566,6 +566,8 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   L.wait(L.chain, L.misc[0]);
   L.record(L.misc[1], L.upd);
   L.wait(L.chain, L.misc[1]);
+  L.record(L.row_rest[0], L.chain2);
+  L.wait(L.chain, L.row_rest[0]);
   //      Same look-ahead as the factorisation: the chain lane updates only the block row the next
   //      back-substitution needs, the upd lane the rows above it.
   for (int64_t pi = panels - 1, it = 0; pi >= 0; --pi, ++it) {

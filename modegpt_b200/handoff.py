@@ -33,7 +33,7 @@ _SLICE = 64 << 20
 
 
 class LayerWriter:
-    def __init__(self, n_threads: int = 6, max_in_flight: int = 12):
+    def __init__(self, n_threads: int = 6, max_in_flight: int = 12, device=None):
         self._stage_q: queue.Queue = queue.Queue()
         self._save_q: queue.Queue = queue.Queue()
         self._slots = threading.Semaphore(max_in_flight)
@@ -45,6 +45,7 @@ class LayerWriter:
         if hasattr(ser, "set_crc32_options") and hasattr(ser, "get_crc32_options"):
             self._crc_prev = ser.get_crc32_options()
             ser.set_crc32_options(False)
+        self._warm_device = torch.device(device) if device is not None else None   # pin the bounce buffers now
         self._threads = [threading.Thread(target=self._stager, daemon=True, name="mg-stager")]
         self._threads += [threading.Thread(target=self._saver, daemon=True, name=f"mg-saver-{i}")
                           for i in range(n_threads)]
@@ -84,6 +85,15 @@ class LayerWriter:
     # ------------------------------------------------------------------------------------------
     def _stager(self) -> None:
         stream, bounce, events = None, None, None
+        if self._warm_device is not None and self._warm_device.type == "cuda":
+            try:
+                torch.cuda.set_device(self._warm_device)   # threads start on device 0: keep rank r on GPU r
+                stream = torch.cuda.Stream(device=self._warm_device)
+                bounce = [torch.empty(_SLICE, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+                events = [torch.cuda.Event() for _ in range(2)]
+            except BaseException as e:
+                self._errors.append(e)
+                stream = None
         while True:
             job = self._stage_q.get()
             if job is None:
@@ -94,6 +104,7 @@ class LayerWriter:
                 if ready is not None:
                     dev = next(w.device for w in weights.values() if w.is_cuda)
                     if stream is None or stream.device != dev:
+                        torch.cuda.set_device(dev)
                         stream = torch.cuda.Stream(device=dev)
                         bounce = [torch.empty(_SLICE, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
                         events = [torch.cuda.Event() for _ in range(2)]

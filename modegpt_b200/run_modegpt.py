@@ -121,6 +121,7 @@ def main(trial=None, config: CompressionConfig | None = None):
         logger.info(f"Baseline ppl: {baseline}")
         adapter.metrics["baseline-ppl"] = baseline
 
+    adapter.prepare_writer()      # writer threads + 128 MB of pinned bounce buffers, before the timed stages
     n_layers = adapter.n_layers
     save_dir = os.path.join(config.output_dir, "model")
     rotary_masks: list = []
@@ -191,6 +192,9 @@ def main(trial=None, config: CompressionConfig | None = None):
     # the layer files are written behind the decompositions (handoff.LayerWriter); the wait for the
     # last of them belongs to the compression stage ("compress s/layer incl. file write")
     timed("file_flush_s", adapter.flush_saves)
+    if D.world_size() > 1:
+        logger.info(f"[rank {D.rank()}] calibration {timings['calibration_s']:.2f}s mlp {timings['mlp_s']:.2f}s "
+                    f"qk {timings['qk_s']:.2f}s vo {timings['vo_s']:.2f}s flush {timings['file_flush_s']:.2f}s")
     D.barrier()   # every owner has written its layer files
     tokens = config.calib_size * config.seq_len
     # stages may overlap: the wall time of the whole decomposition phase is what counts
