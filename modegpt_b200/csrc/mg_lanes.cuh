@@ -1,16 +1,22 @@
 // mg_lanes.cuh — the internal "lanes" (CUDA streams) a blocked factorisation is spread over.
 //
 // A right-looking blocked Cholesky is a chain of small, latency-bound panel kernels (potrf128 ->
-// trsm128) followed by a wide trailing update; run on one stream, the GPU idles behind the chain.
-// The drivers in mg_linalg.cu / mg_type1.cu therefore fork the caller's stream into
-//   chain : high priority — potrf128, trsm128 and the look-ahead update of the next block row;
-//   upd   : the rest of each trailing update (one panel behind the chain);
-//   tri   : work that only consumes finished block rows (triangular inverse rows, the Nystrom
-//           cross term and its forward substitution);
-//   tri2  : the part of a triangular-inverse row that does not depend on the previous row
-//           (look-ahead for the tri lane's own chain);
+// trsm128) followed by wide updates; run on one stream, the GPU idles behind the chain.  The
+// drivers in mg_linalg.cu / mg_type1.cu therefore fork the caller's stream into
+//   chain  : high priority — only what the next potrf128 needs: potrf128, the solve of the first
+//            384 columns of the block row, one 128 x 384 tile update;
+//   chain2 : high priority — the rest of the block row's solve and of the outer block's row
+//            updates (overlaps the next potrf128);
+//   upd    : the K = 512 update of everything below an outer block (once per 4 panels), the
+//            2-CTA diagonal solves of the triangular inverse, the back-substitution updates;
+//   tri    : work that only consumes finished block rows (triangular-inverse rows, the Nystrom
+//            cross term and its forward substitution);
+//   tri2   : the part of a triangular-inverse row that does not depend on the previous row
+//            (look-ahead for the tri lane's own chain);
 // and join them back before returning, so to the caller every entry point is still an ordinary
-// stream-ordered call.  Streams and events are created once per device (no memory is allocated).
+// stream-ordered call.  Hand-offs are CUDA events; adds into the same rows are ordered, so results
+// do not depend on timing.  Streams and events are created once per device, two sets of them, so
+// two host threads can run two factorisations side by side (no memory is allocated).
 // MG_SERIAL=1 collapses all lanes onto the caller's stream (A/B measurements, debugging).
 #pragma once
 #include <cuda_runtime.h>

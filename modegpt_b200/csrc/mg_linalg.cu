@@ -532,11 +532,14 @@ struct DeviceLanes {
   Lanes proto;
 };
 
-DeviceLanes& device_lanes() {
-  static DeviceLanes per_dev[64];
+// Two independent lane sets per device: two host threads can run two factorisations side by side
+// (different layers; each chain is latency-bound and leaves most SMs idle).
+constexpr int kLaneSets = 2;
+DeviceLanes& device_lanes(int slot) {
+  static DeviceLanes per_dev[64][kLaneSets];
   int dev = 0;
   cudaGetDevice(&dev);
-  return per_dev[dev & 63];
+  return per_dev[dev & 63][slot];
 }
 
 int chol_outer_panels() {
@@ -571,8 +574,14 @@ LaneScope::LaneScope(cudaStream_t user) {
   lanes_.user = lanes_.chain = lanes_.chain2 = lanes_.upd = lanes_.tri = lanes_.tri2 = user;
   lanes_.serial = true;
   if (lanes_disabled()) return;
-  DeviceLanes& d = device_lanes();
-  d.mu.lock();
+  DeviceLanes* dp = nullptr;
+  for (int slot = 0; slot < kLaneSets && !dp; ++slot)
+    if (device_lanes(slot).mu.try_lock()) dp = &device_lanes(slot);
+  if (!dp) {
+    dp = &device_lanes(0);
+    dp->mu.lock();
+  }
+  DeviceLanes& d = *dp;
   lock_ = &d;
   if (!d.tried) {
     d.tried = true;

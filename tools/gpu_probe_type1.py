@@ -32,6 +32,19 @@ for _ in range(reps):
     torch.cuda.synchronize()
     tr += ev[0].elapsed_time(ev[1]); tn += e2.elapsed_time(ev[2])
 print(f"ridge_ms={tr/reps:.2f} nystrom_ms={tn/reps:.2f}")
+# host side: how long the library call itself takes to enqueue everything (returns before the GPU is done)
+from modegpt_b200._lib import lib
+import modegpt_b200.ops as _ops
+acc = {"mg_ridge_scores_f32": 0.0, "mg_nystrom_down_f32": 0.0}
+for name in acc:
+    real = getattr(lib, name)
+    def timed(*a, _real=real, _name=name):
+        t0 = time.perf_counter(); rc = _real(*a); acc[_name] += time.perf_counter() - t0; return rc
+    setattr(_ops.lib, name, timed)
+torch.cuda.synchronize()
+for _ in range(reps):
+    run(); torch.cuda.synchronize()
+print("host_enqueue_ms " + " ".join(f"{k}={1e3*v/reps:.2f}" for k, v in acc.items()))
 torch.save({"s": s.cpu(), "idx": idx.cpu(), "out": out.cpu()}, sys.argv[5])
 """
 
