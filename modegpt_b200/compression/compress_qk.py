@@ -44,9 +44,9 @@ def compress_qk(adapter: ModelAdapter, cov, keep_ratios, rank=None, slice_dims=T
     if not slice_dims:
         return None
     if D.is_distributed():
-        merged = D.gather_by_layer({k: v.cpu() for k, v in local.items()}, adapter.n_layers)
         device = next(adapter.model.parameters()).device
-        return [merged[i].to(device) for i in target_layers if merged[i] is not None]
+        merged = D.gather_masks(local, adapter.n_layers, adapter.n_kv_heads, hd, device)
+        return [merged[i] for i in target_layers if merged[i] is not None]
     return [local[i] for i in target_layers if i in local]
 
 

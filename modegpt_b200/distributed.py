@@ -75,6 +75,31 @@ def gather_by_layer(local: dict, n_layers: int) -> list:
     return [merged.get(i) for i in range(n_layers)]
 
 
+def gather_masks(local: dict, n_layers: int, rows: int, width: int, device) -> list:
+    """Rotary masks ([rows, r] int64 with r <= width, one per layer, each owned by one rank) to every
+    rank in layer order: one all-reduce of a padded [n_layers, 2 + rows * width] int64 tensor —
+    each layer has exactly one owner, so the sum is the gather (an object all-gather costs ~0.7 s
+    of pickling and extra collectives per call)."""
+    if not is_distributed():
+        return [local.get(i) for i in range(n_layers)]
+    buf = torch.zeros(n_layers, 2 + rows * width, dtype=torch.int64, device=device)
+    for i, m in local.items():
+        r = m.shape[1]
+        buf[i, 0] = 1
+        buf[i, 1] = r
+        buf[i, 2:2 + rows * r] = m.reshape(-1).to(device)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    head = buf[:, :2].cpu()
+    out = []
+    for i in range(n_layers):
+        if int(head[i, 0]) == 0:
+            out.append(None)
+        else:
+            r = int(head[i, 1])
+            out.append(buf[i, 2:2 + rows * r].reshape(rows, r).clone())
+    return out
+
+
 def barrier() -> None:
     if is_distributed():
         dist.barrier()

@@ -121,7 +121,7 @@ def main(trial=None, config: CompressionConfig | None = None):
         logger.info(f"Baseline ppl: {baseline}")
         adapter.metrics["baseline-ppl"] = baseline
 
-    adapter.prepare_writer()      # writer threads + 128 MB of pinned bounce buffers, before the timed stages
+    adapter.prepare_writer()      # writer threads + 384 MB of pinned bounce buffers, before the timed stages
     n_layers = adapter.n_layers
     save_dir = os.path.join(config.output_dir, "model")
     rotary_masks: list = []

@@ -129,6 +129,12 @@ def _gloo_worker(rank, world, port, out_dir):
     full = D.gather_by_layer({l: torch.tensor([l, rank]) for l in D.owned_layers(range(n_layers))}, n_layers)
     assert [int(x[0]) for x in full] == list(range(n_layers))
     assert [int(x[1]) for x in full] == [l % world for l in range(n_layers)]
+    # rotary masks of ragged rank (r differs per layer) through the padded all-reduce
+    local = {l: torch.arange(2 * (3 + l)).reshape(2, 3 + l) + 100 * l for l in D.owned_layers(range(n_layers))}
+    masks = D.gather_masks(local, n_layers + 1, rows=2, width=8, device="cpu")
+    assert masks[n_layers] is None
+    for l in range(n_layers):
+        assert torch.equal(masks[l], torch.arange(2 * (3 + l)).reshape(2, 3 + l) + 100 * l)
     s = D.all_reduce_sum_(torch.tensor([1.0 + rank]))
     assert s.item() == sum(1.0 + r for r in range(world))
     D.barrier()
