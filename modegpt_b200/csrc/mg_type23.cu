@@ -79,6 +79,15 @@ __global__ void __launch_bounds__(128) qk_select_kernel(const float* __restrict_
 // =================================================================================================
 // type-III: batched symmetric eigensolver + recombination factors
 // =================================================================================================
+// 1/sqrt(x), x > 0: single-precision seed + one third-order correction inside the float range
+// (error 5 e^3 / 16 with e ~ 2^-22), the library routine outside it.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
+  const double y0 = static_cast<double>(rsqrtf(static_cast<float>(x)));
+  const double e = fma(-x * y0, y0, 1.0);
+  return fma(y0 * e, fma(0.375, e, 0.5), y0);
+}
+
 constexpr int kMaxHd = 128;
 
 struct EigSmem {
@@ -186,9 +195,16 @@ __device__ void jacobi_eig(EigSmem& s, int hd) {
         const double gpq = s.g[p * ld + q];
         double c = 1.0, sn = 0.0;
         if (gpq != 0.0) {
-          const double tau = (s.g[q * ld + q] - s.g[p * ld + p]) / (2.0 * gpq);
-          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + tt * tt);
+          // t = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = a / b  ==  sgn(a) b / (|a| + hypot(a, b)):
+          // no division, and the three reciprocal square roots come from a single-precision seed
+          // (this scalar chain runs on 64 threads while the other 960 wait at the barrier)
+          const double a = s.g[q * ld + q] - s.g[p * ld + p], b = 2.0 * gpq;
+          const double r2 = fma(a, a, b * b);
+          const double den = fabs(a) + r2 * rsqrt_pos(r2);
+          const double yd = rsqrt_pos(den);
+          double tt = b * (yd * yd);
+          tt = a < 0.0 ? -tt : tt;
+          c = rsqrt_pos(fma(tt, tt, 1.0));
           sn = tt * c;
         }
         s.cs[2 * t] = c;
@@ -201,28 +217,40 @@ __device__ void jacobi_eig(EigSmem& s, int hd) {
       // blocks are disjoint, G stays symmetric, and only its upper triangle (row <= column) is
       // stored and touched — each 2 x 2 block is read, rotated on both sides and written back
       // by one thread (block (l, k) is the mirror image and is never formed)
+      // (all loads of the thread's blocks first, then the arithmetic and the stores: the blocks are
+      //  disjoint, but the compiler cannot hoist a load of s.g above a store to s.g by itself)
+      double gv[kMaxBlocksPerThread][4];
+      int go[kMaxBlocksPerThread][4];      // element offsets inside s.g (upper-triangle addressing)
 #pragma unroll
       for (int b = 0; b < kMaxBlocksPerThread; ++b) {
         const int kl = my_blocks[b];
-        if (kl < 0) break;
+        if (kl < 0) continue;
         const int k = kl >> 8, l = kl & 255;
         const int pk = s.pq[2 * k], qk = s.pq[2 * k + 1];
         const int pl = s.pq[2 * l], ql = s.pq[2 * l + 1];
+        go[b][0] = pk <= pl ? pk * ld + pl : pl * ld + pk;
+        go[b][1] = pk <= ql ? pk * ld + ql : ql * ld + pk;
+        go[b][2] = qk <= pl ? qk * ld + pl : pl * ld + qk;
+        go[b][3] = qk <= ql ? qk * ld + ql : ql * ld + qk;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) gv[b][x] = s.g[go[b][x]];
+      }
+#pragma unroll
+      for (int b = 0; b < kMaxBlocksPerThread; ++b) {
+        const int kl = my_blocks[b];
+        if (kl < 0) continue;
+        const int k = kl >> 8, l = kl & 255;
         const double ck = s.cs[2 * k], sk = s.cs[2 * k + 1];
         const double cl = s.cs[2 * l], sl = s.cs[2 * l + 1];
-        double* e_pp = s.g + (pk <= pl ? pk * ld + pl : pl * ld + pk);
-        double* e_pq = s.g + (pk <= ql ? pk * ld + ql : ql * ld + pk);
-        double* e_qp = s.g + (qk <= pl ? qk * ld + pl : pl * ld + qk);
-        double* e_qq = s.g + (qk <= ql ? qk * ld + ql : ql * ld + qk);
-        const double gpp = *e_pp, gpq = *e_pq, gqp = *e_qp, gqq = *e_qq;
+        const double gpp = gv[b][0], gpq = gv[b][1], gqp = gv[b][2], gqq = gv[b][3];
         // right rotation (columns pl, ql)
         const double a_pp = cl * gpp - sl * gpq, a_pq = sl * gpp + cl * gpq;
         const double a_qp = cl * gqp - sl * gqq, a_qq = sl * gqp + cl * gqq;
         // left rotation (rows pk, qk)
-        *e_pp = ck * a_pp - sk * a_qp;
-        *e_pq = ck * a_pq - sk * a_qq;
-        *e_qp = sk * a_pp + ck * a_qp;
-        *e_qq = sk * a_pq + ck * a_qq;
+        s.g[go[b][0]] = ck * a_pp - sk * a_qp;
+        s.g[go[b][1]] = ck * a_pq - sk * a_qq;
+        s.g[go[b][2]] = sk * a_pp + ck * a_qp;
+        s.g[go[b][3]] = sk * a_pq + ck * a_qq;
       }
       // V <- V J  (rows p, q of the transposed store)
       const int quads = hd / 4;
@@ -232,11 +260,14 @@ __device__ void jacobi_eig(EigSmem& s, int hd) {
         const double c = s.cs[2 * k], sn = s.cs[2 * k + 1];
         float4* rp = reinterpret_cast<float4*>(s.v + p * ldv) + i4;
         float4* rq = reinterpret_cast<float4*>(s.v + q * ldv) + i4;
+        // V is stored in fp32; rotating it in fp32 too (instead of widening every component) costs
+        // one extra rounding per update and removes 16 conversions per pair from the slow pipe
+        const float cf = static_cast<float>(c), sf = static_cast<float>(sn);
         const float4 vp = *rp, vq = *rq;
-        *rp = make_float4(static_cast<float>(c * vp.x - sn * vq.x), static_cast<float>(c * vp.y - sn * vq.y),
-                          static_cast<float>(c * vp.z - sn * vq.z), static_cast<float>(c * vp.w - sn * vq.w));
-        *rq = make_float4(static_cast<float>(sn * vp.x + c * vq.x), static_cast<float>(sn * vp.y + c * vq.y),
-                          static_cast<float>(sn * vp.z + c * vq.z), static_cast<float>(sn * vp.w + c * vq.w));
+        *rp = make_float4(fmaf(cf, vp.x, -sf * vq.x), fmaf(cf, vp.y, -sf * vq.y),
+                          fmaf(cf, vp.z, -sf * vq.z), fmaf(cf, vp.w, -sf * vq.w));
+        *rq = make_float4(fmaf(sf, vp.x, cf * vq.x), fmaf(sf, vp.y, cf * vq.y),
+                          fmaf(sf, vp.z, cf * vq.z), fmaf(sf, vp.w, cf * vq.w));
       }
       __syncthreads();
     }
