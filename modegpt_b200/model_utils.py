@@ -1,7 +1,7 @@
 """Model I/O for the compression flow (reference: src/model_utils.py).
 
 `reload_compressed_model` / `save_compressed_model` keep the reference's call shapes.  Additions:
-`synthetic:<preset>` model names build random-init models of the real shapes (no hub access), the
+`synthetic:<preset>[:<n_layers>]` model names build random-init models of the real shapes (no hub access), the
 tokenizer is optional, and the rotary-mask path is stored relative to the checkpoint so a saved
 model can be moved (the reference stores an absolute path).
 """
@@ -76,7 +76,11 @@ def reload_compressed_model(model_dir: str, device="cuda:0", tokenizer_source: s
 
     logger.info(f"Loading model from: {model_dir}")
     if model_dir.startswith("synthetic:"):
-        return build_synthetic_model(model_dir.split(":", 1)[1], device=device), None
+        # synthetic:<preset>[:<n_layers>] — real widths, optionally fewer layers (70B-class shapes
+        # on one GPU)
+        parts = model_dir.split(":")
+        n_layers = int(parts[2]) if len(parts) > 2 and parts[2] else None
+        return build_synthetic_model(parts[1], device=device, n_layers=n_layers), None
     src = tokenizer_source
     if not src:
         marker = os.path.join(model_dir, "tokenizer_source.txt")
