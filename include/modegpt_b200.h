@@ -12,7 +12,13 @@
  *     (ws, ws_bytes) and have a `*_ws_bytes` query.
  *   - return value: 0 = OK; < 0 = argument error (-1000 - cudaError_t for CUDA runtime errors);
  *     > 0 = numerical info (1-based index of the first non-positive pivot).
- *   - asynchronous: work is enqueued on `stream`; no host synchronisation unless stated.
+ *   - asynchronous and stream-ordered: to the caller every entry point behaves as one operation
+ *     enqueued on `stream`; no host synchronisation unless stated.  The two blocked type-I entry
+ *     points (mg_ridge_scores_f32, mg_nystrom_down_f32) fork `stream` into internal streams
+ *     ("lanes", created once per device; events only, no memory) and join them before returning,
+ *     so their panel chain, trailing updates and triangular-inverse / substitution work overlap.
+ *     Two lane sets exist per device: two host threads may call them concurrently; a third
+ *     concurrent call waits for a set.  MG_SERIAL=1 keeps everything on `stream`.
  *   - matrices are row-major.  "upper" = elements with col >= row are defined; the strict lower
  *     triangle is unspecified unless the function says it mirrors.
  */
@@ -61,9 +67,10 @@ int mg_scale_f32(float* x, int64_t count, float scale, void* stream);
 
 /* ---- type-I: Nystrom MLP ---------------------------------------------------------------------- */
 
-/* scores[j] = diag((C + ridge I)^-1)_j.  C: fp32 [n,n], upper triangle read.  Blocked Cholesky
- * (fp64 128-wide diagonal blocks, tcgen05 TRSM + trailing SYRK on bf16x3 planes) and blocked
- * triangular inverse.  *info (device int, caller zero-initialises) receives the 1-based index of
+/* scores[j] = diag((C + ridge I)^-1)_j.  C: fp32 [n,n], upper triangle read.  Two-level blocked
+ * Cholesky (fp64 128-wide diagonal blocks, fused triangular-solve panels, tcgen05 updates on bf16x3
+ * planes: K = 128 inside an outer block of 4 panels, K = 512 below it) and a blocked triangular
+ * inverse that runs concurrently, one panel behind.  *info (device int, caller zero-initialises) receives the 1-based index of
  * the first non-positive pivot, else stays 0.
  * Replaces get_ridge_scores, src/compression/compress_mlp.py:13-25. */
 size_t mg_ridge_scores_ws_bytes(int64_t n);
