@@ -1,3 +1,5 @@
 set -x
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 -m modegpt_b200.run_modegpt --model synthetic:llama-3-8b --order mlp,qk,vo --compression_ratio 0.25 --calib_size 128 --calibs_batch_size 16 --nystrom_ridge 1e-4 --ridge_vo 1e-5 --ridge_qk 1e-2 --sparsity_smoothing 0.04948 --max_sparsity 0.95 --dataset synthetic --output_dir /tmp/e2e_out8 --temp_storage_dir /tmp/e2e_out8/layers/ > gpurun_out/c21_e2e_llama3_8b_n8.log 2>&1
-grep "rank \|stages:\|calibration \|Compressed (PPL)\|Baseline\|Error" gpurun_out/c21_e2e_llama3_8b_n8.log | tail -14
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/c22_pytest.log
+timeout 900 python bench.py > gpurun_out/c22_bench.json 2> gpurun_out/c22_bench.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c22_smoke.log 2>&1
+tail -3 gpurun_out/c22_pytest.log; cat gpurun_out/c22_bench.json; tail -2 gpurun_out/c22_smoke.log
