@@ -20,6 +20,7 @@
 // MG_SERIAL=1 collapses all lanes onto the caller's stream (A/B measurements, debugging).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace mg {
 
@@ -38,6 +39,7 @@ struct Lanes {
   cudaEvent_t bulk_done[2] = {nullptr, nullptr};  // look-ahead part of the row's cross product
   cudaEvent_t misc[2] = {nullptr, nullptr};
   bool serial = true;
+  int reserve_sms = 48;   // SMs kept free of persistent bulk CTAs (see LaneScope)
 
   void record(cudaEvent_t e, cudaStream_t on) const {
     if (!serial) cudaEventRecord(e, on);
@@ -52,7 +54,9 @@ struct Lanes {
 // destruction.  `ok()` is false if the streams could not be created; the drivers then run serial.
 class LaneScope {
  public:
-  explicit LaneScope(cudaStream_t user);
+  // `n` = order of the matrix being factored: small problems are bound by the panel chain (keep
+  // a third of the SMs free for it), large ones by the bulk GEMMs (give them nearly everything).
+  LaneScope(cudaStream_t user, int64_t n);
   ~LaneScope();
   LaneScope(const LaneScope&) = delete;
   LaneScope& operator=(const LaneScope&) = delete;

@@ -561,16 +561,18 @@ bool lanes_disabled() {
 }  // namespace
 
 int Lanes::bulk_cta_cap() const {
-  static const int reserve = [] {
-    const char* e = std::getenv("MG_BULK_RESERVE_SMS");   // SMs kept free of persistent bulk CTAs
-    const int v = e ? std::atoi(e) : 48;   // measured: Nystrom 12.8 -> 11.7 ms from 4 -> 52, ridge flat
-    return v < 0 ? 0 : v;
-  }();
-  const int cap = device_sm_count() - reserve;
+  const int cap = device_sm_count() - reserve_sms;
   return serial ? 0 : (cap < 16 ? 16 : cap);
 }
 
-LaneScope::LaneScope(cudaStream_t user) {
+LaneScope::LaneScope(cudaStream_t user, int64_t n) {
+  // measured at n = 11008: Nystrom 12.8 -> 11.7 ms going from 4 to 52 reserved SMs (chain-bound);
+  // at n = 28672 the bulk GEMMs are the bound (574 TFLOP/s on 100 CTAs) and want the SMs back
+  static const int reserve_env = [] {
+    const char* e = std::getenv("MG_BULK_RESERVE_SMS");
+    return e ? std::atoi(e) : -1;
+  }();
+  const int reserve = reserve_env >= 0 ? reserve_env : (n > 16384 ? 8 : 48);
   lanes_.user = lanes_.chain = lanes_.chain2 = lanes_.upd = lanes_.tri = lanes_.tri2 = user;
   lanes_.serial = true;
   if (lanes_disabled()) return;
@@ -608,6 +610,7 @@ LaneScope::LaneScope(cudaStream_t user) {
   lanes_ = d.proto;
   lanes_.user = user;
   lanes_.serial = false;
+  lanes_.reserve_sms = reserve;
   cudaEventRecord(lanes_.fork, user);
   cudaStreamWaitEvent(lanes_.chain, lanes_.fork, 0);
   cudaStreamWaitEvent(lanes_.upd, lanes_.fork, 0);

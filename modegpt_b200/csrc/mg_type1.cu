@@ -71,7 +71,9 @@ struct NystromWs {
   bf16* wdt;        // [n x dp]        W_down^T
   float* rhs;       // [k x dp]        cross term -> Z -> X (in place)
   float* ckk;       // [k x kp]
-  bf16* z_planes;   // [2][3][128 x dp]
+  bf16* z_planes;   // [3][128 x dp]      X planes of one panel (single-stream back-substitution)
+  bf16* zb_planes;  // [3][4*128 x dp]    forward substitution: Z planes of one outer block
+  bf16* xb_planes;  // [2][3][4*128 x dp] back-substitution: X planes of an outer block (double-buffered)
   mg::CholWorkspace chol;
   size_t bytes;
 };
@@ -85,7 +87,9 @@ NystromWs carve_nystrom(void* p, int64_t n, int64_t k, int64_t d) {
   w.wdt = c.take<bf16>(n * dp);
   w.rhs = c.take<float>(k * dp);
   w.ckk = c.take<float>(k * kp);
-  w.z_planes = c.take<bf16>(2 * kPlanes * kNB * dp);   // double-buffered: look-ahead overlaps two panels
+  w.z_planes = c.take<bf16>(kPlanes * kNB * dp);        // single-stream path only
+  w.zb_planes = c.take<bf16>(kPlanes * 4 * kNB * dp);
+  w.xb_planes = c.take<bf16>(2 * kPlanes * 4 * kNB * dp);
   w.chol.u_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.l_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
@@ -315,7 +319,7 @@ int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, flo
   const int64_t np = w.chol.n_pad;
   int rc;
 
-  mg::LaneScope scope(s);
+  mg::LaneScope scope(s, n);
   const mg::Lanes& L = scope.lanes();
 
   copy_ridge_kernel<<<dim3(static_cast<unsigned>((n + 1023) / 1024 < 8 ? (n + 1023) / 1024 : 8),
@@ -472,7 +476,7 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   const int64_t kp = w.chol.n_pad, dp = mg::round_up(d, 64);
   int rc;
 
-  mg::LaneScope scope(s);
+  mg::LaneScope scope(s, k);
   const mg::Lanes& L = scope.lanes();
 
   // tri lane: operands of the cross term  rhs[k, d] = C[idx, :] W_down^T = (C[:, idx])^T (W_down^T)
@@ -523,6 +527,12 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   mg::CholStepper chol{w.ckk, k, kp, w.chol, info, &L};
   // ---- forward solve  U^T Z = rhs  (right-looking, in place) rides one panel behind the
   //      factorisation on the tri lane: step pi needs block row pi of U and nothing later
+  //      Two-level blocking like the factorisation: inside an outer block of kFwdOuter panels a
+  //      panel only updates the block's remaining rows (K = 128); the rows below the block get one
+  //      update per block with K = kFwdOuter * 128 from the block's stacked Z planes — a quarter
+  //      of the read-modify-write passes over rhs.
+  constexpr int64_t kFwdOuter = 4;
+  const int64_t zb_stride = kFwdOuter * kNB * dp;      // plane stride of the stacked Z block
   for (int64_t pi = 0; pi < panels; ++pi) {
     if ((rc = chol.step(pi))) return rc;
     L.wait(L.tri, L.trsm);
@@ -530,34 +540,46 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
     const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
     float* bi = w.rhs + i0 * dp;
     const int64_t rest = k - i0 - nb;
-    // Z_i = U_ii^-T B_i (+ planes of Z_i for the update below)
+    const int64_t q = pi % kFwdOuter, o0 = (pi - q) * kNB;
+    const int64_t o_end = (o0 + kFwdOuter * kNB < k) ? o0 + kFwdOuter * kNB : k;
+    bf16* zq = w.zb_planes + q * kNB * dp;              // this panel's rows inside the Z block
+    // Z_i = U_ii^-T B_i (+ planes of Z_i for the updates below)
     MG_TIMED(L.tri, "nystrom.fwd_trsm",
              rc = mg::trsm128(w.chol.t_fwd + pi * mg::kTBlock, false, nb, bi, dp, d, 1.f, bi, dp,
-                              rest > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
-                              L.tri));
+                              rest > 0 ? zq : nullptr, dp, zb_stride, nullptr, 0, 0, nullptr, L.tri));
     if (rc) return rc;
     if (rest <= 0) break;
     mg::GemmArgs t{};
-    t.A = w.chol.u_planes + i0 * kp + (i0 + nb);  // B[rest] -= U[ib, rest]^T Z_i
     t.lda = kp;
     t.a_plane_stride = pstride;
     t.a_planes = kPlanes;
-    t.B = w.z_planes;
     t.ldb = dp;
-    t.b_plane_stride = kNB * dp;
+    t.b_plane_stride = zb_stride;
     t.b_planes = kPlanes;
     pairs6(t);
-    t.M = rest;
     t.N = d;
-    t.K = nb;
-    t.D = w.rhs + (i0 + nb) * dp;
     t.ldd = dp;
     t.alpha = -1.f;
     t.tiles = mg::TILES_FULL;
     t.epi = mg::EPI_ADD;
     t.ksplit = 1;
     t.max_ctas = L.bulk_cta_cap();
-    MG_TIMED(L.tri, "nystrom.fwd_update", rc = mg::gemm_tn_launch(t, L.tri));
+    const int64_t in_block = o_end - (i0 + nb);
+    if (in_block > 0) {            // B[block rows below] -= U[ib, those rows]^T Z_i
+      t.A = w.chol.u_planes + i0 * kp + (i0 + nb);
+      t.B = zq;
+      t.M = in_block;
+      t.K = nb;
+      t.D = w.rhs + (i0 + nb) * dp;
+      MG_TIMED(L.tri, "nystrom.fwd_update_in_block", rc = mg::gemm_tn_launch(t, L.tri));
+    } else {                       // B[rows below the block] -= U[block rows, those rows]^T Z_block
+      t.A = w.chol.u_planes + o0 * kp + o_end;
+      t.B = w.zb_planes;
+      t.M = rest;
+      t.K = o_end - o0;
+      t.D = w.rhs + o_end * dp;
+      MG_TIMED(L.tri, "nystrom.fwd_update", rc = mg::gemm_tn_launch(t, L.tri));
+    }
     if (rc) return rc;
   }
   // ---- backward solve  U X = Z  on the chain lane, once the forward pass and every trailing
@@ -568,54 +590,121 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   L.wait(L.chain, L.misc[1]);
   L.record(L.row_rest[0], L.chain2);
   L.wait(L.chain, L.row_rest[0]);
-  //      Same look-ahead as the factorisation: the chain lane updates only the block row the next
-  //      back-substitution needs, the upd lane the rows above it.
-  for (int64_t pi = panels - 1, it = 0; pi >= 0; --pi, ++it) {
-    const int64_t i0 = pi * kNB;
-    const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
-    float* zi = w.rhs + i0 * dp;
-    MG_TIMED(L.chain, "nystrom.bwd_trsm",
-             rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
-                              i0 > 0 ? w.z_planes + (it & 1) * kPlanes * kNB * dp : nullptr, dp, kNB * dp,
-                              nullptr, 0, 0, nullptr, L.chain));
-    if (rc) return rc;
-    if (i0 == 0) break;
-    L.record(L.trsm, L.chain);
-    mg::GemmArgs t{};
-    t.lda = kp;
-    t.a_plane_stride = pstride;
-    t.a_planes = kPlanes;
-    t.B = w.z_planes + (it & 1) * kPlanes * kNB * dp;
-    t.ldb = dp;
-    t.b_plane_stride = kNB * dp;
-    t.b_planes = kPlanes;
-    pairs6(t);
-    t.N = d;
-    t.K = nb;
-    t.ldd = dp;
-    t.alpha = -1.f;
-    t.tiles = mg::TILES_FULL;
-    t.epi = mg::EPI_ADD;
-    t.ksplit = 1;
-    // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
-    const int64_t m1 = L.serial ? 0 : kNB;          // i0 is a multiple of 128
-    if (i0 - m1 > 0) {
-      mg::GemmArgs r = t;
-      r.A = w.chol.l_planes + i0 * kp;
-      r.M = i0 - m1;
-      r.D = w.rhs;
-      r.max_ctas = L.bulk_cta_cap();
-      L.wait(L.upd, L.trsm);
-      MG_TIMED(L.upd, "nystrom.bwd_update", rc = mg::gemm_tn_launch(r, L.upd));
+  //      Two-level blocking + look-ahead, mirrored from the factorisation (panels run from the
+  //      last to the first): inside an outer block a panel only updates the block's rows above it
+  //      (K = 128, chain lane); when the block's first panel is solved, the rows above the block
+  //      get the whole block at once (K = 512) — the next block's last block row on the chain
+  //      lane, its other rows and everything above on the upd lane.
+  if (L.serial) {
+    for (int64_t pi = panels - 1; pi >= 0; --pi) {
+      const int64_t i0 = pi * kNB;
+      const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+      float* zi = w.rhs + i0 * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_trsm",
+               rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
+                                i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
+                                L.chain));
       if (rc) return rc;
-      L.record(L.upd_done[it & 1], L.upd);
+      if (i0 == 0) break;
+      mg::GemmArgs t{};
+      t.A = w.chol.l_planes + i0 * kp;   // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
+      t.lda = kp;
+      t.a_plane_stride = pstride;
+      t.a_planes = kPlanes;
+      t.B = w.z_planes;
+      t.ldb = dp;
+      t.b_plane_stride = kNB * dp;
+      t.b_planes = kPlanes;
+      pairs6(t);
+      t.M = i0;
+      t.N = d;
+      t.K = nb;
+      t.D = w.rhs;
+      t.ldd = dp;
+      t.alpha = -1.f;
+      t.tiles = mg::TILES_FULL;
+      t.epi = mg::EPI_ADD;
+      t.ksplit = 1;
+      MG_TIMED(L.chain, "nystrom.bwd_update", rc = mg::gemm_tn_launch(t, L.chain));
+      if (rc) return rc;
     }
-    if (m1 > 0) {
-      if (it >= 1) L.wait(L.chain, L.upd_done[(it - 1) & 1]);   // ordered adds into block row pi-1
-      t.A = w.chol.l_planes + i0 * kp + (i0 - m1);
-      t.M = m1;
-      t.D = w.rhs + (i0 - m1) * dp;
-      MG_TIMED(L.chain, "nystrom.bwd_row_update", rc = mg::gemm_tn_launch(t, L.chain));
+  } else {
+    const int64_t nblocks = (panels + kFwdOuter - 1) / kFwdOuter;
+    for (int64_t pi = panels - 1; pi >= 0; --pi) {
+      const int64_t i0 = pi * kNB;
+      const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+      const int64_t ob = pi / kFwdOuter, o0 = ob * kFwdOuter * kNB;
+      const int64_t o_end = (o0 + kFwdOuter * kNB < k) ? o0 + kFwdOuter * kNB : k;
+      // X planes of the block, stacked by row (double-buffered by block parity: the upd lane may
+      // still read block ob while the chain lane fills block ob-1)
+      bf16* xb = w.xb_planes + (ob & 1) * kPlanes * zb_stride;
+      bf16* xq = xb + (i0 - o0) * dp;
+      float* zi = w.rhs + i0 * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_trsm",
+               rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
+                                i0 > 0 ? xq : nullptr, dp, zb_stride, nullptr, 0, 0, nullptr, L.chain));
+      if (rc) return rc;
+      if (i0 == 0) break;
+      mg::GemmArgs t{};
+      t.lda = kp;
+      t.a_plane_stride = pstride;
+      t.a_planes = kPlanes;
+      t.ldb = dp;
+      t.b_plane_stride = zb_stride;
+      t.b_planes = kPlanes;
+      pairs6(t);
+      t.N = d;
+      t.ldd = dp;
+      t.alpha = -1.f;
+      t.tiles = mg::TILES_FULL;
+      t.epi = mg::EPI_ADD;
+      t.ksplit = 1;
+      const int64_t above = i0 - o0;                  // rows of this block above panel pi
+      if (above > 0) {
+        // (ordered adds) the block below updated these rows from the upd lane
+        if (i0 + nb >= o_end && ob + 1 < nblocks) L.wait(L.chain, L.next_done[(ob + 1) & 1]);
+        t.A = w.chol.l_planes + i0 * kp + o0;         // A[k, m] = L[i0 + k, o0 + m] = U[o0 + m, i0 + k]
+        t.B = xq;
+        t.M = above;
+        t.K = nb;
+        t.D = w.rhs + o0 * dp;
+        MG_TIMED(L.chain, "nystrom.bwd_update_in_block", rc = mg::gemm_tn_launch(t, L.chain));
+        if (rc) return rc;
+        continue;
+      }
+      // pi is the block's first panel: rows [0, o0) get the whole block (K = o_end - o0)
+      t.K = o_end - o0;
+      t.B = xb;
+      const int64_t first = kNB;                      // o0 is a multiple of 4 * 128
+      const int64_t next_rows = kFwdOuter * kNB;      // rows of the block above (all of them exist)
+      L.record(L.trsm, L.chain);
+      L.wait(L.upd, L.trsm);
+      {
+        mg::GemmArgs r = t;                           // block above, except its last block row
+        r.A = w.chol.l_planes + o0 * kp + (o0 - next_rows);
+        r.M = next_rows - first;
+        r.D = w.rhs + (o0 - next_rows) * dp;
+        r.max_ctas = L.bulk_cta_cap();
+        MG_TIMED(L.upd, "nystrom.bwd_update_next", rc = mg::gemm_tn_launch(r, L.upd));
+        if (rc) return rc;
+        L.record(L.next_done[ob & 1], L.upd);
+      }
+      if (o0 - next_rows > 0) {                       // everything above that block
+        mg::GemmArgs r = t;
+        r.A = w.chol.l_planes + o0 * kp;
+        r.M = o0 - next_rows;
+        r.D = w.rhs;
+        r.max_ctas = L.bulk_cta_cap();
+        MG_TIMED(L.upd, "nystrom.bwd_update", rc = mg::gemm_tn_launch(r, L.upd));
+        if (rc) return rc;
+      }
+      L.record(L.upd_done[ob & 1], L.upd);
+      // chain: the last block row of the block above (the next panel to be solved)
+      if (ob + 1 < nblocks) L.wait(L.chain, L.upd_done[(ob + 1) & 1]);
+      t.A = w.chol.l_planes + o0 * kp + (o0 - first);
+      t.M = first;
+      t.D = w.rhs + (o0 - first) * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_update_first", rc = mg::gemm_tn_launch(t, L.chain));
       if (rc) return rc;
     }
   }
