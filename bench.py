@@ -333,15 +333,6 @@ def run_gpu_arm(args) -> None:
                         "ms_per_layer": stage_ms, "layers_timed": len(layers),
                         "note": "type I (n=11008, r=8256) + II + III (MHA, 32 heads) per layer, "
                                 "in-memory hand-off"}
-            # the three stages side by side, as run_modegpt runs them (one thread + stream each)
-            from modegpt_b200.run_modegpt import _run_stages_concurrent
-
-            tim = {"mlp_s": 0.0, "qk_s": 0.0, "vo_s": 0.0, "compress_wall_s": 0.0}
-            _run_stages_concurrent(
-                {"mlp_s": lambda: compress_nystrom(adapter, cov_mlp, keep, layers),
-                 "qk_s": lambda: compress_qk(adapter, (cov_q, cov_k), keep, target_layers=layers),
-                 "vo_s": lambda: compress_vo(adapter, cov_x, keep, target_layers=layers)}, tim, str(dev))
-            compress["s_per_layer_concurrent_stages"] = tim["compress_wall_s"] / len(layers)
             # the same stages writing the reference's layer_{i}_{mlp,qk,vo} files through the
             # asynchronous writer, final flush included (a full run hides the writes of all but
             # the last layers behind the next layers' kernels; with so few layers it cannot)
