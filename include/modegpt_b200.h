@@ -124,6 +124,20 @@ int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, in
                    int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* The same operation in two stream-ordered halves that share `ws` (mg_vo_ws_bytes):
+ *   mg_vo_prepare : the tensor-core part — G1[h] = W_v,h (Cx + ridge I) W_v,h^T and, for MHA,
+ *                   G2[h] = W_o,h^T W_o,h — left in the workspace;
+ *   mg_vo_finish  : the per-head eigensolves (one CTA per kv head, milliseconds) and the
+ *                   recombination of the old heads into Wv_out / Wo_out.
+ * A caller that prepares several layers back to back and then finishes them on different streams
+ * overlaps their eigensolves (each uses n_kv_heads of the SMs); mg_vo_compress is prepare + finish. */
+int mg_vo_prepare(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
+                  const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
+                  void* ws, size_t ws_bytes, void* stream);
+int mg_vo_finish(const void* Wv, int64_t ldwv, const void* Wo, int64_t ldwo, int n_heads,
+                 int n_kv_heads, int hd, int64_t d, int r, void* Wv_out, int64_t ldv_out,
+                 void* Wo_out, int64_t ldo_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- calibration forward: fused elementwise kernels ------------------------ */
 
 /* y[r, :] = weight * bf16(x32[r, :] * rsqrt(mean(x32[r, :]^2) + eps)), every intermediate rounded

@@ -39,6 +39,9 @@ SIGNATURES: dict[str, tuple] = {
     "mg_vo_ws_bytes": (C.c_size_t, [i64, i32, i32, i32]),
     "mg_vo_compress": (i32, [vp, i64, f32, vp, i64, vp, i64, i32, i32, i32, i64, i32, vp, i64,
                              vp, i64, vp, C.c_size_t, vp]),
+    "mg_vo_prepare": (i32, [vp, i64, f32, vp, i64, vp, i64, i32, i32, i32, i64, vp, C.c_size_t, vp]),
+    "mg_vo_finish": (i32, [vp, i64, vp, i64, i32, i32, i32, i64, i32, vp, i64, vp, i64, vp,
+                           C.c_size_t, vp]),
     "mg_rmsnorm_bf16": (i32, [vp, i64, i64, i64, vp, f32, vp, i64, vp]),
     "mg_swiglu_bf16": (i32, [vp, vp, vp, i64, vp]),
     "mg_rope_bf16": (i32, [vp, vp, vp, vp, i64, i64, i32, i32, i64, vp]),

@@ -25,45 +25,52 @@ logger = logging.getLogger("MoDeGPT")
 @torch.no_grad()
 def compress_vo(adapter: ModelAdapter, cov, keep_ratios=None, slice_dims=True,
                 target_layers: list[int] | None = None):
+    """Layer loop + `save_layer(suffix="vo")` (compress_vo.py:13-109).
+
+    The per-head eigensolver runs one CTA per kv head for milliseconds (32 of 148 SMs for an MHA
+    layer, 8 for a GQA one).  Layers are therefore taken in groups: the tensor-core halves
+    (`mg_vo_prepare`) of a group run back to back on the caller's stream, then the eigensolver halves
+    (`mg_vo_finish`) are issued on one stream per layer so they run side by side; the group is
+    joined before the next one starts, so a persistent GEMM grid never has to share the GPU with
+    long-running eigensolver CTAs.  `--vo_group 1` keeps one `mg_vo_compress` per layer."""
     if target_layers is None:
         target_layers = list(range(adapter.n_layers))
     H, KV, hd = adapter.n_heads, adapter.n_kv_heads, adapter.head_dim
     layers = list(D.owned_layers(target_layers))
-    # The per-head eigensolver runs one CTA per kv head (32 of 148 SMs for an MHA layer, 8 for a
-    # GQA one) and nothing in this function synchronises with the host, so with `--vo_streams N`
-    # consecutive layers are issued round-robin on N CUDA streams and their eigensolves can run
-    # side by side.  Opt-in: measured 0.30 -> 0.14 s for 32 Llama-2-7B layers in one run and 9.4 ->
-    # 16.9 ms/layer in another — a persistent GEMM grid of the next layer that cannot be fully
-    # resident next to the eigensolver CTAs leaves its unplaced CTAs' tiles waiting (the engine
-    # strides tiles statically); it needs a dynamic tile scheduler to be dependable.
-    streams, caller = [None], None
-    if layers and cov[layers[0]].is_cuda and getattr(adapter.config, "vo_streams", 1) != 1:
-        device = cov[layers[0]].device
-        n_streams = getattr(adapter.config, "vo_streams", 1) or max(2, min(8, 128 // max(KV, 1)))
-        caller = torch.cuda.current_stream(device)
+    group = getattr(adapter.config, "vo_group", 0) or max(1, min(8, 128 // max(KV, 1)))
+    if group <= 1 or not layers or not cov[layers[0]].is_cuda:
+        for layer in layers:
+            _compress_layer(adapter, cov, keep_ratios, layer, H, KV, hd)
+        return
+    device = cov[layers[0]].device
+    caller = torch.cuda.current_stream(device)
+    streams = _side_streams(device, group)
+    for g0 in range(0, len(layers), group):
+        chunk = layers[g0:g0 + group]
+        prepared = [_prepare_layer(adapter, cov, keep_ratios, layer, H, KV, hd) for layer in chunk]
         ready = torch.cuda.Event()
         ready.record(caller)
-        streams = [torch.cuda.Stream(device=device) for _ in range(min(n_streams, len(layers)))]
+        for st, item in zip(streams, prepared):
+            if item is None:
+                continue
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                _finish_layer(adapter, item, H, KV, hd)
         for st in streams:
-            st.wait_event(ready)       # statistics / weights were produced on the caller's stream
-    try:
-        _compress_layers(adapter, cov, keep_ratios, layers, streams, H, KV, hd)
-    finally:
-        if caller is not None:
-            for st in streams:
-                caller.wait_stream(st)
+            caller.wait_stream(st)
 
 
-def _compress_layers(adapter, cov, keep_ratios, layers, streams, H, KV, hd):
-    import contextlib
-
-    for n, layer in enumerate(layers):
-        st = streams[n % len(streams)]
-        with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
-            _compress_layer(adapter, cov, keep_ratios, layer, H, KV, hd)
+_STREAMS: dict = {}
 
 
-def _compress_layer(adapter, cov, keep_ratios, layer, H, KV, hd):
+def _side_streams(device, n: int) -> list:
+    pool = _STREAMS.setdefault(torch.device(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def _layer_inputs(adapter, keep_ratios, layer, hd):
     # same rule as Q/K so the rebuilt attention has ONE head dim per layer (SURVEY A.2);
     # the reference does not clamp the V/O rank to head_dim (compress_vo.py:36-41).
     rank_i = min(head_rank(hd, keep_ratios[layer], adapter.uses_rope, clamp_to_head=False), hd)
@@ -72,9 +79,38 @@ def _compress_layer(adapter, cov, keep_ratios, layer, H, KV, hd):
         wv, wo = comps.v_proj.weight.detach(), comps.o_proj.weight.detach()
     except AttributeError as e:     # the reference skips such layers too (compress_vo.py:47-53)
         logger.warning(f"[VO] Layer {layer}: cannot access v_proj/o_proj: {e}")
+        return None
+    return rank_i, comps, wv.contiguous(), wo.contiguous()
+
+
+def _prepare_layer(adapter, cov, keep_ratios, layer, H, KV, hd):
+    got = _layer_inputs(adapter, keep_ratios, layer, hd)
+    if got is None:
+        return None
+    rank_i, comps, wv, wo = got
+    ws = ops.vo_prepare(cov[layer], adapter.config.ridge_vo, wv, wo, H, KV, hd)
+    return layer, rank_i, comps, wv, wo, ws, ops.vo_outputs(wv, H, KV, rank_i)
+
+
+def _finish_layer(adapter, item, H, KV, hd):
+    layer, rank_i, comps, wv, wo, ws, out = item
+    here = torch.cuda.current_stream(ws.device)
+    for t in (ws, *out):                                     # allocated on the caller's stream
+        t.record_stream(here)
+    v_new, o_new = ops.vo_finish(ws, wv, wo, H, KV, hd, rank_i, out=out)
+    _save(adapter, layer, rank_i, comps, wo, v_new, o_new, H, KV, hd)
+
+
+def _compress_layer(adapter, cov, keep_ratios, layer, H, KV, hd):
+    got = _layer_inputs(adapter, keep_ratios, layer, hd)
+    if got is None:
         return
-    v_new, o_new = ops.vo_compress(cov[layer], adapter.config.ridge_vo, wv.contiguous(),
-                                   wo.contiguous(), H, KV, hd, rank_i)
+    rank_i, comps, wv, wo = got
+    v_new, o_new = ops.vo_compress(cov[layer], adapter.config.ridge_vo, wv, wo, H, KV, hd, rank_i)
+    _save(adapter, layer, rank_i, comps, wo, v_new, o_new, H, KV, hd)
+
+
+def _save(adapter, layer, rank_i, comps, wo, v_new, o_new, H, KV, hd):
     weights = {"v_proj": v_new, "o_proj": o_new}
     bv, bo = getattr(comps.v_proj, "bias", None), getattr(comps.o_proj, "bias", None)
     if bo is not None or bv is not None:

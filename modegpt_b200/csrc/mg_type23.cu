@@ -545,17 +545,13 @@ size_t mg_vo_ws_bytes(int64_t d, int n_heads, int n_kv_heads, int hd) {
   return carve_vo(nullptr, d, n_heads, n_kv_heads, hd).bytes;
 }
 
-int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
-                   const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
-                   int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
-                   size_t ws_bytes, void* stream) {
-  if (!Cx || !Wv || !Wo || !Wv_out || !Wo_out || !ws) return -1;
+int mg_vo_prepare(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
+                  const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
+                  void* ws, size_t ws_bytes, void* stream) {
+  if (!Cx || !Wv || !Wo || !ws) return -1;
   if (d <= 0 || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads) return -2;
   if (hd != 32 && hd != 64 && hd != 128) return -6;
-  if (r <= 0 || r > hd) return -11;
-  if (ldc < d || ldwv < d || ldwo < static_cast<int64_t>(n_heads) * hd || ldv_out < d ||
-      ldo_out < static_cast<int64_t>(n_heads) * r)
-    return -7;
+  if (ldc < d || ldwv < d || ldwo < static_cast<int64_t>(n_heads) * hd) return -7;
   VoWs w = carve_vo(ws, d, n_heads, n_kv_heads, hd);
   if (ws_bytes < w.bytes) return -10;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -634,6 +630,27 @@ int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, in
                                 stream);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int mg_vo_finish(const void* Wv, int64_t ldwv, const void* Wo, int64_t ldwo, int n_heads,
+                 int n_kv_heads, int hd, int64_t d, int r, void* Wv_out, int64_t ldv_out,
+                 void* Wo_out, int64_t ldo_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!Wv || !Wo || !Wv_out || !Wo_out || !ws) return -1;
+  if (d <= 0 || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads) return -2;
+  if (hd != 32 && hd != 64 && hd != 128) return -6;
+  if (r <= 0 || r > hd) return -11;
+  if (ldwv < d || ldwo < static_cast<int64_t>(n_heads) * hd || ldv_out < d ||
+      ldo_out < static_cast<int64_t>(n_heads) * r)
+    return -7;
+  VoWs w = carve_vo(ws, d, n_heads, n_kv_heads, hd);
+  if (ws_bytes < w.bytes) return -10;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int group = n_heads / n_kv_heads;
+  const bool mha = group == 1;
+  const bf16* wv = static_cast<const bf16*>(Wv);
+  const bf16* wo = static_cast<const bf16*>(Wo);
+  int rc;
   static bool attr_set = false;
   const size_t esm = eig_smem_bytes(hd);
   const size_t osm = sizeof(float) * (hd * r + 64 * (hd + 1));
@@ -659,6 +676,19 @@ int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, in
   vo_apply_o_kernel<<<dim3(static_cast<unsigned>((d + 63) / 64), n_heads), 256, osm, s>>>(
       wo, ldwo, w.ro, group, hd, r, d, static_cast<bf16*>(Wo_out), ldo_out);
   return cuda_rc();
+}
+
+int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
+                   const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
+                   int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
+                   size_t ws_bytes, void* stream) {
+  if (!Wv_out || !Wo_out) return -1;
+  if (r <= 0 || r > hd) return -11;
+  int rc = mg_vo_prepare(Cx, ldc, ridge, Wv, ldwv, Wo, ldwo, n_heads, n_kv_heads, hd, d, ws, ws_bytes,
+                         stream);
+  if (rc) return rc;
+  return mg_vo_finish(Wv, ldwv, Wo, ldwo, n_heads, n_kv_heads, hd, d, r, Wv_out, ldv_out, Wo_out,
+                      ldo_out, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -220,6 +220,46 @@ def vo_compress(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tens
     return v_out, o_out
 
 
+def vo_prepare(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int,
+               n_kv_heads: int, hd: int) -> torch.Tensor:
+    """First half of `vo_compress` (the tensor-core part); returns the workspace for `vo_finish`."""
+    d, ldc = _f32_square(Cx, "Cx")
+    _, _, ldwv = _rowmajor_2d(Wv, "Wv")
+    _, _, ldwo = _rowmajor_2d(Wo, "Wo")
+    if Wv.dtype != torch.bfloat16 or Wo.dtype != torch.bfloat16:
+        raise TypeError("vo_prepare: weights must be bfloat16")
+    if Wv.shape != (n_kv_heads * hd, d) or Wo.shape != (d, n_heads * hd):
+        raise ValueError("vo_prepare: weight shapes do not match the head layout")
+    nbytes = lib.mg_vo_ws_bytes(d, n_heads, n_kv_heads, hd)
+    ws = _workspace(nbytes, Cx.device)
+    check("mg_vo_prepare",
+          lib.mg_vo_prepare(Cx.data_ptr(), ldc, ridge, Wv.data_ptr(), ldwv, Wo.data_ptr(), ldwo,
+                            n_heads, n_kv_heads, hd, d, ws.data_ptr(), nbytes, _stream()))
+    return ws
+
+
+def vo_outputs(Wv: torch.Tensor, n_heads: int, n_kv_heads: int, r: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Output buffers of `vo_finish` (v_proj [KV*r, d], o_proj [d, H*r]).  Allocating them up front,
+    on the caller's stream, keeps `vo_finish` free of allocations: a first allocation on a fresh
+    side stream is a cudaMalloc, which synchronises the device and would serialise the streams."""
+    d = Wv.shape[1]
+    return (torch.empty(n_kv_heads * r, d, dtype=torch.bfloat16, device=Wv.device),
+            torch.empty(d, n_heads * r, dtype=torch.bfloat16, device=Wv.device))
+
+
+def vo_finish(ws: torch.Tensor, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int, n_kv_heads: int,
+              hd: int, r: int, out: tuple[torch.Tensor, torch.Tensor] | None = None
+              ) -> tuple[torch.Tensor, torch.Tensor]:
+    """Second half of `vo_compress`: per-head eigensolves + recombination, on the current stream."""
+    d = Wv.shape[1]
+    v_out, o_out = out if out is not None else vo_outputs(Wv, n_heads, n_kv_heads, r)
+    check("mg_vo_finish",
+          lib.mg_vo_finish(Wv.data_ptr(), Wv.stride(0), Wo.data_ptr(), Wo.stride(0), n_heads, n_kv_heads,
+                           hd, d, r, v_out.data_ptr(), v_out.stride(0), o_out.data_ptr(),
+                           o_out.stride(0), ws.data_ptr(), ws.numel(), _stream()))
+    return v_out, o_out
+
+
 # ------------------------------------------------------------------------------------------------
 # calibration forward: fused elementwise kernels
 # ------------------------------------------------------------------------------------------------

@@ -248,3 +248,25 @@ def test_type1_workers_do_not_change_results(golden, tmp_path):
         for name in ("up", "gate"):
             assert torch.equal(out[1][key][name], out[2][key][name])
         assert rel(out[2][key]["down"].float().cpu().numpy(), out[1][key]["down"].float().cpu().numpy()) < 2e-3
+
+
+def test_type3_grouped_layers_match_one_at_a_time(golden, tmp_path):
+    """compress_vo in groups (mg_vo_prepare back to back, mg_vo_finish on one stream per layer) is
+    the same computation as one mg_vo_compress per layer: bit-identical tensors."""
+    from modegpt_b200.compression.compress_vo import compress_vo
+
+    g = golden("pipeline_llama_mha")
+    L = int(g["cfg"][2])
+    f32 = lambda k: torch.tensor(g[k], device=DEV, dtype=torch.float32)
+    keep = [float(x) for x in g["keep"]]
+    out = {}
+    for group in (1, 0, 2):
+        adapter = make_adapter(g, tmp_path, keep_layers_in_memory=True, vo_group=group)
+        compress_vo(adapter, [f32(f"cov_x{l}") for l in range(L)], keep, target_layers=list(range(L)))
+        torch.cuda.synchronize()
+        out[group] = dict(adapter._layer_store)
+    for group in (0, 2):
+        assert set(out[group]) == set(out[1]) == {(l, "vo") for l in range(L)}
+        for key in out[1]:
+            for name in ("v_proj", "o_proj"):
+                assert torch.equal(out[1][key][name], out[group][key][name])
