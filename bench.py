@@ -6,10 +6,12 @@
 
 A step = one calibration batch (calibs_batch_size 16 x 2048 synthetic tokens) through the hooked
 bf16 forward of a random-init Llama-2-7B with every statistics kernel firing (C_mlp, C_x, per-head
-C_q / C_k, Block-Influence) — the hot loop of src/calibration.py:114-127.  `value` times it with the
-token batch already in HBM; `e2e` re-times it with the tokens in pinned host memory (H2D inside)
-and the BI scores read back (D2H inside).  After the timed steps the statistics are finalised and
-`--compress-layers` layers go through type I/II/III to report seconds per layer.
+C_q / C_k, Block-Influence) — the hot loop of src/calibration.py:114-127.  `value` times K such steps with the
+token batches already in HBM, plus the cross-rank exchange and the final normalise/mirror; `e2e` is
+the same work through the public API `load_calibs` on pinned host batches (H2D inside, BI scores
+read back).  `strong_scaling` runs the real configuration (128 x 2048 tokens in total) through
+`load_calibs`, and its statistics feed `compress`: every layer through type I/II/III by its owner
+rank, layer files written, max-over-ranks wall per layer.
 
 `--impl reference` (and the `cpu_baseline` object of the default arm) time the reference's algorithm
 for the same path — the fp64 restatement in oracle/ — on the host cores, on a bounded sample.
@@ -39,18 +41,20 @@ HYPER = dict(compression_ratio=0.25, nystrom_ridge=1e-4, ridge_vo=1e-5, ridge_qk
 
 
 def ncu_traffic_bytes():
-    """DRAM bytes (read + write) of one C_mlp SYRK launch from the committed ncu --set full capture."""
-    p = ROOT / "profiles" / "r1_syrk_pair_banded_ncu_full.json"
-    if not p.exists():
-        return None
+    """DRAM bytes (read + write) of one C_mlp SYRK launch from the newest committed ncu --set full
+    capture of the kernel (tools/summarize_ncu.py output), and the file it came from."""
+    cands = sorted((ROOT / "profiles").glob("r*_syrk*_ncu_full.json"), reverse=True)
+    if not cands:
+        return None, None
+    p = cands[0]
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     best = None
     for k in json.loads(p.read_text())["kernels"]:
         if "gemm_tn" not in k["kernel"]:
             continue
         tot = sum(float(k[m]["value"]) * mult[k[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        best = max(best or 0.0, tot)      # the n = 11008 launch is the largest <256> launch captured
-    return best
+        best = max(best or 0.0, tot)      # the n = 11008 launch is the largest launch captured
+    return best, f"profiles/{p.name}"
 
 
 def peaks():
@@ -133,6 +137,61 @@ def cpu_reference_sample(t_slice: int = 2048, seed: int = 0) -> dict:
                       f"{t_slice} tokens in {wall:.2f} s, scaled by 1/{LAYERS} layers; model forward excluded"}
 
 
+def cpu_compress_sample(seed: int = 0) -> dict:
+    """The compress half of the metric on the host cores: the oracle's `nystrom_mlp`
+    (compress_mlp.py:28-64), `qk_layer` (compress_qk.py:208-308) and the type-III layer body
+    (compress_vo.py:43-99) once each at the full Llama-2-7B shape, fp64, all host threads.
+    Type III is sampled: sqrt_M + inverse of the 4096^2 statistic once, then 2 of the 32 heads,
+    scaled to 32 (every head costs the same: two SVDs, the second a full 128 x 4096 one)."""
+    from threadpoolctl import threadpool_limits
+
+    from oracle import modegpt_oracle as O
+
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    keep = 1.0 - HYPER["compression_ratio"]
+
+    def spd(n, rank=256):
+        a = rng.standard_normal((n, rank))
+        return a @ a.T / rank + np.diag(np.exp(rng.standard_normal(n)))
+
+    with threadpool_limits(limits=cores):
+        c_mlp = spd(D_INT)
+        w_up = rng.standard_normal((D_INT, D)) * 0.02
+        w_gate = rng.standard_normal((D_INT, D)) * 0.02
+        w_down = rng.standard_normal((D, D_INT)) * 0.02
+        t0 = time.perf_counter()
+        O.nystrom_mlp(w_up, w_gate, w_down, c_mlp, keep, HYPER["nystrom_ridge"])
+        t_mlp = time.perf_counter() - t0
+        del c_mlp, w_up, w_gate, w_down
+        c_q = np.stack([spd(HD, 32) for _ in range(HEADS)])
+        c_k = np.stack([spd(HD, 32) for _ in range(KV)])
+        w_q = rng.standard_normal((HEADS * HD, D)) * 0.02
+        w_k = rng.standard_normal((KV * HD, D)) * 0.02
+        r = O.head_rank(HD, keep, True)
+        t0 = time.perf_counter()
+        O.qk_layer(w_q, w_k, c_q, c_k, HEADS, KV, HD, r, "llama", HYPER["ridge_qk"])
+        t_qk = time.perf_counter() - t0
+        c_x = spd(D)
+        w_v = rng.standard_normal((KV * HD, D)) * 0.02
+        w_o = rng.standard_normal((D, HEADS * HD)) * 0.02
+        t0 = time.perf_counter()
+        root, root_inv = O.vo_roots(c_x, HYPER["ridge_vo"])
+        t_root = time.perf_counter() - t0
+        sample_heads = 2
+        t0 = time.perf_counter()
+        for h in range(sample_heads):
+            O.vo_head_mha(w_v[h * HD:(h + 1) * HD], w_o[:, h * HD:(h + 1) * HD], root, root_inv, r)
+        t_head = (time.perf_counter() - t0) / sample_heads
+        t_vo = t_root + t_head * HEADS
+    return {"s_per_layer": t_mlp + t_qk + t_vo, "unit": "s/layer", "cores": cores, "kind": "port",
+            "ms_per_layer": {"mlp": 1e3 * t_mlp, "qk": 1e3 * t_qk, "vo": 1e3 * t_vo},
+            "sample": f"fp64 oracle, one Llama-2-7B layer: nystrom_mlp n=11008 r={int(D_INT * keep)} "
+                      f"({t_mlp:.1f} s), qk_layer 32 heads ({t_qk:.2f} s), type III = sqrt_M+inv of 4096^2 "
+                      f"({t_root:.1f} s) + {sample_heads} of {HEADS} heads timed ({t_head:.2f} s each) "
+                      f"scaled to {HEADS}; no file write"}
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -146,12 +205,14 @@ def run_reference_arm(args) -> None:
     ms = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
     v = float(np.mean([x["value"] for x in vals]))
     base = dict(vals[-1], value=v)
+    base["compress"] = cpu_compress_sample()
     print(json.dumps({
         "impl": "reference", "metric": "calib_tokens_per_s", "value": v, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": base,
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "compress": {"s_per_layer": base["compress"]["s_per_layer"], "ms_per_layer": base["compress"]["ms_per_layer"]},
     }))
 
 
@@ -159,7 +220,8 @@ def workload_config(n_gpus: int) -> dict:
     return {"workload": "Llama-2-7B 25% MoDeGPT calibration, 16x2048 synthetic tokens per step "
                         "(BASELINE configs[1]); random-init weights",
             "calibs_batch_size": BATCH, "seq_len": SEQ, "layers": LAYERS,
-            "parallelism": f"token-sharded x{n_gpus}, one reduce-to-owner per layer at the end",
+            "parallelism": f"token-sharded x{n_gpus}; each layer's sums packed (upper triangles) and "
+                           f"reduced to its owner during the last local batch; layers decomposed by owner",
             "l2_policy": "inputs larger than L2 (each statistics operand is 268-721 MB)",
             "forward": "HF modules, fused RMSNorm/SwiGLU/RoPE kernels (bit-compatible)", **HYPER}
 
@@ -168,13 +230,21 @@ def workload_config(n_gpus: int) -> dict:
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu_arm(args) -> None:
+    import gc
+    import shutil
+    import tempfile
+
     import torch.distributed as dist
 
-    from modegpt_b200 import distributed as Dm
+    import modegpt_b200.adapters.model_adapter as MA
     from modegpt_b200 import ops
     from modegpt_b200.adapters.CompressionConfig import CompressionConfig
     from modegpt_b200.adapters.model_adapter import ModelAdapter
-    from modegpt_b200.fused_forward import fused_elementwise
+    from modegpt_b200.calibration import Calibrator, load_calibs
+    from modegpt_b200.compression.compress_mlp import compress_nystrom
+    from modegpt_b200.compression.compress_qk import compress_qk
+    from modegpt_b200.compression.compress_vo import compress_vo
+    from modegpt_b200.compression_utils import allocate_global_sparsity
     from modegpt_b200.model_utils import build_synthetic_model
 
     rank = int(os.environ.get("RANK", "0"))
@@ -189,24 +259,30 @@ def run_gpu_arm(args) -> None:
     model = build_synthetic_model(PRESET, device=str(dev), seed=0)
     adapter = ModelAdapter.from_model(model, tokenizer=None)
     adapter.config = CompressionConfig(model=f"synthetic:{PRESET}", dataset="synthetic", order="mlp,qk,vo",
-                                       calib_size=128, calibs_batch_size=BATCH, keep_layers_in_memory=True,
+                                       calib_size=128, calibs_batch_size=BATCH, eager_forward=args.eager_forward,
                                        **HYPER)
-    body = model.model                      # the LM head is not on the calibration path
-    blocks = adapter.get_transformer_blocks()
-    f32 = dict(dtype=torch.float32, device=dev)
-    cov_mlp = [torch.zeros(D_INT, D_INT, **f32) for _ in range(LAYERS)]
-    cov_x = [torch.zeros(D, D, **f32) for _ in range(LAYERS)]
-    cov_q = [torch.zeros(HEADS, HD, HD, **f32) for _ in range(LAYERS)]
-    cov_k = [torch.zeros(KV, HD, HD, **f32) for _ in range(LAYERS)]
-    handles: list = []
-    for i in range(LAYERS):
-        adapter.register_hooks(i, blocks[i], cov_mlp, cov_q, cov_k, cov_x, handles, None)
-    bi = torch.zeros(LAYERS, dtype=torch.float64, device=dev)
-    adapter.register_bi_hooks(bi, handles)
+    all_layers = list(range(LAYERS))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def release():
+        gc.collect()
+        torch.cuda.empty_cache()
 
     # time the dominant kernel (the 11008-wide SYRK) live: events around every C_mlp launch
     syrk_events: list = []
     real_syrk = ops.syrk_
+    recording = [False]
 
     def timed_syrk(C, X, alpha=1.0, accumulate=True):
         if C.shape[0] == D_INT and recording[0]:
@@ -218,162 +294,160 @@ def run_gpu_arm(args) -> None:
         else:
             real_syrk(C, X, alpha, accumulate)
 
-    recording = [False]
-    ops.syrk_ = timed_syrk
-    import modegpt_b200.adapters.model_adapter as MA
-    MA.ops.syrk_ = timed_syrk
-
     steps_total = args.warmup + args.steps
     vocab = model.config.vocab_size
     g = torch.Generator().manual_seed(1234 + rank)
-    host_tokens = [torch.randint(0, vocab, (BATCH, SEQ), generator=g).pin_memory() for _ in range(steps_total)]
-    dev_tokens = [t.to(dev) for t in host_tokens]
+    dev_tokens = [torch.randint(0, vocab, (BATCH, SEQ), generator=g).to(dev) for _ in range(steps_total)]
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    import contextlib
-
-    fuse = contextlib.nullcontext if args.eager_forward else (lambda: fused_elementwise(model))
-
-    @torch.no_grad()
-    def step(tokens):
-        with fuse():
-            body(tokens, use_cache=False)
-
-    def reduce_all():
-        for i in range(LAYERS):
-            for lst in (cov_mlp, cov_x, cov_q, cov_k):
-                Dm.reduce_to_owner(lst[i], i)
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident timing
-    with torch.no_grad():
+    # ---- A. device-resident: K hooked forwards + the cross-rank exchange + normalise/mirror
+    ops.syrk_ = MA.ops.syrk_ = timed_syrk
+    try:
+        cal = Calibrator(adapter, all_layers)
         for w in range(args.warmup):
-            step(dev_tokens[w])
+            cal.run_batch(dev_tokens[w])
         sync_all()
         recording[0] = True
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_fwd = torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clocks:
             s.record()
             for k in range(args.steps):
-                step(dev_tokens[args.warmup + k])
-            if world > 1:
-                reduce_all()        # the one exchange step of token-sharded calibration
+                cal.run_batch(dev_tokens[args.warmup + k], last=(k == args.steps - 1))
+            s_fwd.record()
+            recording[0] = False
+            stats_a = cal.finish()        # join the reductions, BI all-reduce, scale + mirror
             e.record()
             sync_all()
-        recording[0] = False
+    finally:
+        ops.syrk_ = MA.ops.syrk_ = real_syrk
     ms_total = max_over_ranks(s.elapsed_time(e))
+    ms_tail = max_over_ranks(s_fwd.elapsed_time(e))
     tokens_per_step = BATCH * SEQ * world
     value = tokens_per_step * args.steps / (ms_total * 1e-3)
     syrk_ms = float(np.mean([a.elapsed_time(b) for a, b in syrk_events])) if syrk_events else float("nan")
     syrk_share = float(np.sum([a.elapsed_time(b) for a, b in syrk_events])) / s.elapsed_time(e)
     flops_per_launch = BATCH * SEQ * D_INT * (D_INT + 1)      # upper triangle, 2 flop / MAC
     achieved = flops_per_launch / (syrk_ms * 1e-3) / 1e12
+    del stats_a, cal, dev_tokens
+    release()
 
-    # ---- end to end: pinned host tokens in, BI scores out, every step
-    host_bi = torch.empty(LAYERS, dtype=torch.float64).pin_memory()
-    with torch.no_grad():
+    # ---- B. end to end through the public API: load_calibs() on PINNED HOST token batches
+    # (H2D of every batch, hooked forwards, exchange, normalise/mirror, BI scores read back)
+    def host_batches(n_batches, seed):
+        gg = torch.Generator().manual_seed(seed)
+        return [torch.randint(0, vocab, (BATCH, SEQ), generator=gg).pin_memory() for _ in range(n_batches)]
+
+    def timed_load_calibs(batches):
+        adapter.calibs = batches
         sync_all()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s2.record()
-        for k in range(args.steps):
-            tok = host_tokens[args.warmup + k].to(dev, non_blocking=True)
-            step(tok)
-            host_bi.copy_(bi, non_blocking=True)
-        if world > 1:
-            reduce_all()
+        out = load_calibs(adapter, n_samples=len(batches) * BATCH, batch_size=BATCH, dataset="synthetic",
+                          target_layers=all_layers)
         e2.record()
         sync_all()
-    e2e_ms = max_over_ranks(s2.elapsed_time(e2))
+        return max_over_ranks(s2.elapsed_time(e2)), out
+
+    e2e_ms, stats_b = timed_load_calibs(host_batches(args.steps * world, 4321))
     e2e_value = tokens_per_step * args.steps / (e2e_ms * 1e-3)
-    for h in handles:
-        h.remove()
-    ops.syrk_ = real_syrk
-    MA.ops.syrk_ = real_syrk
+    del stats_b
+    release()
 
-    # ---- compression seconds per layer (type I / II / III on this rank's first layers)
+    # ---- C. strong scaling at the real configuration: BASELINE configs[1]'s 128 x 2048 tokens in
+    # total, split over the ranks, again through load_calibs; its statistics feed the compress stage
+    n_real = 128 // BATCH
+    strong_ms, (cov_mlp, cov_q, cov_k, cov_x, bi_scores) = timed_load_calibs(host_batches(n_real, 1234))
+    strong = {"tokens": 128 * SEQ, "seconds": strong_ms * 1e-3, "tokens_per_s": 128 * SEQ / (strong_ms * 1e-3),
+              "batches_per_rank": n_real / world,
+              "note": "load_calibs on 128x2048 tokens in total (strong scaling; weak scaling is `value`)"}
+
+    # ---- D. compress seconds per layer: type I / II / III of every layer, each by its owner,
+    # layer files written (the metric says "incl. file write"); wall = max over ranks
     compress = None
-    if rank == 0 and args.compress_layers > 0:
-        from modegpt_b200.compression.compress_mlp import compress_nystrom
-        from modegpt_b200.compression.compress_qk import compress_qk
-        from modegpt_b200.compression.compress_vo import compress_vo
+    if args.compress_layers > 0:
+        layers = all_layers[:args.compress_layers]
+        keep = allocate_global_sparsity(bi_scores, compression_ratio=HYPER["compression_ratio"],
+                                        smoothing=HYPER["sparsity_smoothing"],
+                                        max_sparsity=HYPER["max_sparsity"], adapter=adapter)
+        owned = [l for l in layers if l % world == rank]
 
-        n_texts = BATCH * (args.steps * 2 + args.warmup)
-        scale = 1.0 / (n_texts * 2048)
-        layers = list(range(min(args.compress_layers, LAYERS)))
-        for i in layers:
-            ops.finalize_sym_(cov_mlp[i], scale)
-            ops.finalize_sym_(cov_x[i], scale)
-            ops.scale_(cov_q[i], scale)
-            ops.scale_(cov_k[i], scale)
-        keep = [1.0 - HYPER["compression_ratio"]] * LAYERS
-        stage_ms = {}
-        for name, fn in (("mlp", lambda: compress_nystrom(adapter, cov_mlp, keep, layers)),
-                         ("qk", lambda: compress_qk(adapter, (cov_q, cov_k), keep, target_layers=layers)),
-                         ("vo", lambda: compress_vo(adapter, cov_x, keep, target_layers=layers))):
-            if world > 1:
-                break   # ownership would skip layers on rank 0; reported at N = 1 only
-            fn()        # warm (workspace allocation, attribute setup)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fn()
-            torch.cuda.synchronize()
-            stage_ms[name] = (time.perf_counter() - t0) * 1e3 / len(layers)
-        if stage_ms:
-            compress = {"s_per_layer": sum(stage_ms.values()) / 1e3,
-                        "ms_per_layer": stage_ms, "layers_timed": len(layers),
-                        "note": "type I (n=11008, r=8256) + II + III (MHA, 32 heads) per layer, "
-                                "in-memory hand-off"}
-            # the same stages writing the reference's layer_{i}_{mlp,qk,vo} files through the
-            # asynchronous writer, final flush included (a full run hides the writes of all but
-            # the last layers behind the next layers' kernels; with so few layers it cannot)
-            import shutil
-            import tempfile
-
-            tmp = tempfile.mkdtemp(prefix="mg_layers_")
-            adapter.config.keep_layers_in_memory = False
-            adapter.config.temp_storage_dir = tmp
-            try:
+        def stages(which):
+            t = {}
+            for name, fn in (("mlp", lambda: compress_nystrom(adapter, cov_mlp, keep, which)),
+                             ("qk", lambda: compress_qk(adapter, (cov_q, cov_k), keep, target_layers=which)),
+                             ("vo", lambda: compress_vo(adapter, cov_x, keep, target_layers=which))):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                compress_nystrom(adapter, cov_mlp, keep, layers)
-                compress_qk(adapter, (cov_q, cov_k), keep, target_layers=layers)
-                compress_vo(adapter, cov_x, keep, target_layers=layers)
-                adapter.flush_saves()
+                fn()
                 torch.cuda.synchronize()
-                compress["s_per_layer_with_files"] = (time.perf_counter() - t0) / len(layers)
-                compress["file_bytes_per_layer"] = sum(
-                    os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp)) / len(layers)
-            finally:
-                adapter.config.keep_layers_in_memory = True
-                adapter._layer_cache.clear()
-                shutil.rmtree(tmp, ignore_errors=True)
+                t[name] = time.perf_counter() - t0
+            return t
+
+        adapter.config.keep_layers_in_memory = True
+        stages(owned[:1])                        # warm: workspaces, attributes, lanes
+        adapter._layer_store.clear()
+        tmp = tempfile.mkdtemp(prefix="mg_layers_")
+        adapter.config.keep_layers_in_memory = False
+        adapter.config.temp_storage_dir = tmp
+        adapter.prepare_writer()
+        try:
+            sync_all()
+            t0 = time.perf_counter()
+            st_files = stages(layers)            # each stage takes the layers this rank owns
+            tf0 = time.perf_counter()
+            adapter.flush_saves()
+            torch.cuda.synchronize()
+            t_flush = time.perf_counter() - tf0
+            wall_files = max_over_ranks(time.perf_counter() - t0)
+            file_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp))
+        finally:
+            adapter._layer_cache.clear()
+            shutil.rmtree(tmp, ignore_errors=True)
+        adapter.config.keep_layers_in_memory = True
+        sync_all()
+        t0 = time.perf_counter()
+        st_mem = stages(layers)
+        wall_mem = max_over_ranks(time.perf_counter() - t0)
+        adapter._layer_store.clear()
+        n_own = max(len(owned), 1)
+        compress = {
+            "s_per_layer": wall_files / len(layers), "unit": "s/layer",
+            "definition": "max over ranks of wall(type I + II + III of the rank's layers + layer-file "
+                          "writes + final flush) / layers",
+            "layers_timed": len(layers), "layers_per_rank": len(owned),
+            "ms_per_layer_rank0": {k: 1e3 * v / n_own for k, v in st_files.items()},
+            "flush_s_rank0": t_flush, "file_bytes_per_layer": file_bytes / n_own,
+            "in_memory": {"s_per_layer": wall_mem / len(layers),
+                          "ms_per_layer_rank0": {k: 1e3 * v / n_own for k, v in st_mem.items()}},
+            "note": "type I (n=11008, r~8256) + II + III (MHA, 32 heads) per layer; keep ratios from the "
+                    "strong-scaling calibration's BI scores"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    base = cpu_reference_sample(2048) if world == 1 else None
+    base = None
+    if world == 1:
+        base = cpu_reference_sample(2048)
+        base["compress"] = cpu_compress_sample()
+    traffic, traffic_src = ncu_traffic_bytes()
     out = {
         "metric": "calib_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * SEQ * 8,
-                "d2h_bytes_per_step": LAYERS * 8},
-        "gpu_launches": args.steps * LAYERS * (5 if args.eager_forward else 10),
+        "timed_region": "K hooked forwards + cross-rank exchange + BI all-reduce + normalise/mirror "
+                        f"(tail after the last forward: {ms_tail:.1f} ms)",
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * SEQ * 8 * world,
+                "d2h_bytes_per_step": (LAYERS * 8 + 8) * world / args.steps,
+                "api": "modegpt_b200.calibration.load_calibs(adapter, n_samples, batch_size, 'synthetic', "
+                       "target_layers) with adapter.calibs = pinned host batches; BI scores read back once per call"},
+        "strong_scaling": strong,
+        "gpu_launches": args.steps * LAYERS * (5 if args.eager_forward else 10) + 4 * LAYERS,
         "roofline": {"bound": "tensor", "kernel": "gemm_tn_pair_kernel, cta_group::2 256x256 tiles (C_mlp SYRK, n=11008, T=32768)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": ncu_traffic_bytes(),
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "algorithmic_bytes": BATCH * SEQ * D_INT * 2 + D_INT * (D_INT + 1) * 4,
                      "ms_per_launch": syrk_ms, "share_of_step": syrk_share},
         "cpu_baseline": base,
@@ -391,7 +465,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--compress-layers", type=int, default=4)
+    ap.add_argument("--compress-layers", type=int, default=LAYERS,
+                    help="layers put through type I/II/III for the s/layer figure (0 = skip)")
     ap.add_argument("--eager-forward", action="store_true",
                     help="keep HF's eager elementwise kernels in the calibration forward")
     args = ap.parse_args()

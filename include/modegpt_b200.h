@@ -65,6 +65,18 @@ int mg_finalize_sym_f32(float* C, int64_t n, int64_t ldc, float scale, void* str
 /* scale a dense fp32 buffer in place (per-head blocks are already full). */
 int mg_scale_f32(float* x, int64_t count, float scale, void* stream);
 
+/* Wire format of the cross-rank reduction of a symmetric accumulator ("one exchange
+ * step per layer", proposed there as mg_comm_reduce_to_owner).  The SYRK kernels accumulate the
+ * upper triangle of a square fp32 matrix; only n(n+1)/2 values carry information:
+ *   packed[i*n - i*(i-1)/2 + (c - i)] = C[i, c]  for c >= i   (row-major, row i = columns i..n-1).
+ * mg_pack_upper_f32 gathers them into one contiguous buffer (which torch.distributed reduces over
+ * NCCL/NVLink to the layer's owner, one collective per layer, overlapped with the forward of the
+ * following layers), mg_unpack_upper_f32 scatters the sum back into the owner's accumulator; the
+ * strict lower triangle is untouched (mg_finalize_sym_f32 mirrors afterwards).
+ * The reference has no distributed code; this replaces nothing there. */
+int mg_pack_upper_f32(const float* C, int64_t n, int64_t ldc, float* packed, void* stream);
+int mg_unpack_upper_f32(const float* packed, int64_t n, float* C, int64_t ldc, void* stream);
+
 /* ---- type-I: Nystrom MLP ---------------------------------------------------------------------- */
 
 /* scores[j] = diag((C + ridge I)^-1)_j.  C: fp32 [n,n], upper triangle read.  Two-level blocked
@@ -115,17 +127,31 @@ int mg_gather_head_rows_bf16(const void* W, int64_t ldw, const int64_t* mask, in
 
 /* ---- type-III: SVD V/O ----------------------------------------------------------------------- */
 
-/* Wv_out[KV*r, d], Wo_out[d, H*r] (bf16) from Cx [d,d] fp32 FULL symmetric, Wv [KV*hd, d],
- * Wo [d, H*hd] (bf16).  GQA when n_heads != n_kv_heads, else the MHA two-stage form.
- * Replaces compress_vo's per-layer body, src/compression/compress_vo.py:43-99,112-223. */
+/* Wv_out[KV*r, d], Wo_out[d, H*r] (bf16, or fp32 when out_f32 != 0: the unrounded factors, for
+ * accuracy checks) from Cx [d,d] fp32 FULL symmetric, Wv [KV*hd, d], Wo [d, H*hd] (bf16).
+ * GQA when n_heads != n_kv_heads, else the MHA two-stage form.  hd: any multiple of 4 up to 128.
+ * Replaces compress_vo's per-layer body, src/compression/compress_vo.py:43-99,112-223.
+ *
+ * method selects how the hd x hd Gram G1[h] = W_v,h (Cx + ridge I) W_v,h^T (whose eigenpairs are
+ * the right singular pairs of the reference's sqrt(C) W_v,h^T) is obtained:
+ *   MG_VO_FACTOR  Cx + ridge I = U^T U by the blocked Cholesky, M^T = W_v U^T on the tensor cores,
+ *                 G1[h] = M_h^T M_h accumulated in fp64.  Small singular values keep a relative
+ *                 accuracy of ~2^-24 sigma_1/sigma_r.  *info receives the 1-based index of a
+ *                 non-positive pivot (Cx + ridge I numerically singular in fp32): the outputs are
+ *                 then meaningless and the caller should repeat the layer with MG_VO_GRAM.
+ *   MG_VO_GRAM    P = (Cx + ridge I) W_v^T on the tensor cores (fp32), G1[h] = W_v,h P_h in fp64.
+ *                 No factorisation, works for any symmetric Cx; accuracy ~2^-24 (sigma_1/sigma_r)^2.
+ * info is a device pointer (cleared by the call, stream-ordered). */
+#define MG_VO_FACTOR 0
+#define MG_VO_GRAM 1
 size_t mg_vo_ws_bytes(int64_t d, int n_heads, int n_kv_heads, int hd);
 int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
                    const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
-                   int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
-                   size_t ws_bytes, void* stream);
+                   int r, int method, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out,
+                   int out_f32, int* info, void* ws, size_t ws_bytes, void* stream);
 
 /* The same operation in two stream-ordered halves that share `ws` (mg_vo_ws_bytes):
- *   mg_vo_prepare : the tensor-core part — G1[h] = W_v,h (Cx + ridge I) W_v,h^T and, for MHA,
+ *   mg_vo_prepare : factorisation / tensor-core products and the fp64 Grams G1[h] and, for MHA,
  *                   G2[h] = W_o,h^T W_o,h — left in the workspace;
  *   mg_vo_finish  : the per-head eigensolves (one CTA per kv head, milliseconds) and the
  *                   recombination of the old heads into Wv_out / Wo_out.
@@ -133,10 +159,10 @@ int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, in
  * overlaps their eigensolves (each uses n_kv_heads of the SMs); mg_vo_compress is prepare + finish. */
 int mg_vo_prepare(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
                   const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
-                  void* ws, size_t ws_bytes, void* stream);
+                  int method, int* info, void* ws, size_t ws_bytes, void* stream);
 int mg_vo_finish(const void* Wv, int64_t ldwv, const void* Wo, int64_t ldwo, int n_heads,
                  int n_kv_heads, int hd, int64_t d, int r, void* Wv_out, int64_t ldv_out,
-                 void* Wo_out, int64_t ldo_out, void* ws, size_t ws_bytes, void* stream);
+                 void* Wo_out, int64_t ldo_out, int out_f32, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- calibration forward: fused elementwise kernels ------------------------ */
 
@@ -154,6 +180,31 @@ int mg_swiglu_bf16(const void* gate, const void* up, void* out, int64_t count, v
  * (HF apply_rotary_pos_emb; 8 eager kernels per tensor -> 1, bit-exact). */
 int mg_rope_bf16(const void* x, void* out, const void* cos, const void* sin, int64_t batch,
                  int64_t seq, int n_heads, int head_dim, int64_t cos_batch_stride, void* stream);
+
+/* ---- rebuilt-model ops and perplexity -------------------------------- */
+
+/* Masked RoPE of a compressed attention layer: x / out contiguous [batch, seq, n_heads, r] bf16,
+ * cos / sin [*, seq, head_dim] of the ORIGINAL head dim, mask [n_heads / group, r] int64 (the
+ * type-II selection: entries j < r/2 from the first half of the head, j + r/2 their partners).
+ * out[j] = bf16(bf16(x[j] cos[mask[j]]) + bf16(rot(x)[j] sin[mask[j]])), rot = cat(-x[r/2:], x[:r/2]).
+ * Replaces the per-forward `cos[:, :, mask]` gathers + 8 eager kernels of
+ * src/patchers/LlamaRebuild.py:155-180 (bit-exact with that sequence). */
+int mg_rope_masked_bf16(const void* x, void* out, const void* cos, const void* sin,
+                        const int64_t* mask, int64_t batch, int64_t seq, int n_heads, int group, int r,
+                        int head_dim, int64_t cos_batch_stride, void* stream);
+
+/* Qwen3 q_norm / k_norm on compressed heads: x / out contiguous [rows, n_heads, r] bf16, weight
+ * [head_dim] bf16 gathered through mask [n_heads / group, r]; RMS over the r kept dimensions.
+ * Replaces src/patchers/DenseQwenRebuild.py:262-286. */
+int mg_rmsnorm_masked_bf16(const void* x, int64_t rows, int n_heads, int group, int r,
+                           const void* weight, const int64_t* mask, float eps, void* out,
+                           void* stream);
+
+/* nll[row] = logsumexp(logits[row, :vocab]) - logits[row, labels[row]] (fp32) from bf16 logits,
+ * one pass.  The chunked evaluator (eval.compute_perplexity) calls it on row chunks of
+ * hidden @ W_lm^T so [B, T, vocab] fp32 logits never exist (src/eval.py:192-220 formula). */
+int mg_ce_rows_bf16(const void* logits, int64_t ld, int64_t rows, int64_t vocab,
+                    const int64_t* labels, float* nll, void* stream);
 
 #ifdef __cplusplus
 }

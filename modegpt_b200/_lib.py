@@ -27,6 +27,8 @@ SIGNATURES: dict[str, tuple] = {
     "mg_bi_cosine_bf16": (i32, [vp, i64, vp, i64, i64, i64, vp, vp]),
     "mg_finalize_sym_f32": (i32, [vp, i64, i64, f32, vp]),
     "mg_scale_f32": (i32, [vp, i64, f32, vp]),
+    "mg_pack_upper_f32": (i32, [vp, i64, i64, vp, vp]),
+    "mg_unpack_upper_f32": (i32, [vp, i64, vp, i64, vp]),
     "mg_ridge_scores_ws_bytes": (C.c_size_t, [i64]),
     "mg_ridge_scores_f32": (i32, [vp, i64, i64, f32, vp, vp, C.c_size_t, vp, vp]),
     "mg_select_k_f32": (i32, [vp, i64, i64, i32, vp, vp]),
@@ -37,14 +39,18 @@ SIGNATURES: dict[str, tuple] = {
     "mg_qk_select_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp]),
     "mg_gather_head_rows_bf16": (i32, [vp, i64, vp, i32, i32, i64, i64, i64, vp, i64, vp]),
     "mg_vo_ws_bytes": (C.c_size_t, [i64, i32, i32, i32]),
-    "mg_vo_compress": (i32, [vp, i64, f32, vp, i64, vp, i64, i32, i32, i32, i64, i32, vp, i64,
-                             vp, i64, vp, C.c_size_t, vp]),
-    "mg_vo_prepare": (i32, [vp, i64, f32, vp, i64, vp, i64, i32, i32, i32, i64, vp, C.c_size_t, vp]),
-    "mg_vo_finish": (i32, [vp, i64, vp, i64, i32, i32, i32, i64, i32, vp, i64, vp, i64, vp,
+    "mg_vo_compress": (i32, [vp, i64, f32, vp, i64, vp, i64, i32, i32, i32, i64, i32, i32, vp, i64,
+                             vp, i64, i32, vp, vp, C.c_size_t, vp]),
+    "mg_vo_prepare": (i32, [vp, i64, f32, vp, i64, vp, i64, i32, i32, i32, i64, i32, vp, vp,
+                            C.c_size_t, vp]),
+    "mg_vo_finish": (i32, [vp, i64, vp, i64, i32, i32, i32, i64, i32, vp, i64, vp, i64, i32, vp,
                            C.c_size_t, vp]),
     "mg_rmsnorm_bf16": (i32, [vp, i64, i64, i64, vp, f32, vp, i64, vp]),
     "mg_swiglu_bf16": (i32, [vp, vp, vp, i64, vp]),
     "mg_rope_bf16": (i32, [vp, vp, vp, vp, i64, i64, i32, i32, i64, vp]),
+    "mg_rope_masked_bf16": (i32, [vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, i64, vp]),
+    "mg_rmsnorm_masked_bf16": (i32, [vp, i64, i32, i32, i32, vp, vp, f32, vp, vp]),
+    "mg_ce_rows_bf16": (i32, [vp, i64, i64, i64, vp, vp, vp]),
 }
 
 

@@ -218,6 +218,21 @@ class ModelAdapter(ABC):
         return self.arch == "llama" or "qwen" in self.arch
 
     # ---- component getters (same names as the reference's abstract methods) ------------------
+    def validate_for_kernels(self) -> None:
+        """Fail before calibration, with a readable message, on shapes the kernels do not take
+        (the C ABI would otherwise return MG status -6 / -11 in the middle of a run)."""
+        hd = self.head_dim
+        if hd > 128 or hd % 4 != 0:
+            raise NotImplementedError(
+                f"head_dim = {hd}: the type-II / type-III kernels support head dims that are "
+                f"multiples of 4 up to 128 (per-head eigenproblems live in one SM's shared memory)")
+        if self.n_heads % self.n_kv_heads:
+            raise NotImplementedError("n_heads must be a multiple of n_kv_heads")
+        dt = next(self.model.parameters()).dtype
+        if dt != torch.bfloat16:
+            raise TypeError(f"model parameters are {dt}: load through reload_compressed_model "
+                            f"(casts to bfloat16) or call model.to(torch.bfloat16)")
+
     def _block(self, layer_idx: int) -> nn.Module:
         return self.get_transformer_blocks()[layer_idx]
 

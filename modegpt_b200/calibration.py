@@ -29,16 +29,122 @@ def load_calibs(adapter: ModelAdapter, n_samples: int, batch_size: int, dataset:
                             target_layers=target_layers or [])
 
 
+class Calibrator:
+    """The state of one calibration pass (src/calibration.py:39-150): fp32 accumulators for the
+    target layers, the statistics / Block-Influence hooks, and the cross-rank exchange.
+
+        cal = Calibrator(adapter, target_layers)
+        for i, batch in enumerate(batches):
+            cal.run_batch(batch, last=(i == len(batches) - 1))
+        cov_mlp, cov_q, cov_k, cov_x, bi_scores = cal.finish()
+
+    `last=True` arms the reduce-as-you-go exchange: in that batch, as soon as block l has run
+    (all four of its accumulations are enqueued), layer l's sums are packed and reduced to the
+    layer's owner on a side stream (`distributed.LayerReducer`) while the forward continues with
+    block l+1.  Without an armed batch `finish()` submits every layer itself.  `finish()` joins
+    the exchange, normalises by the GLOBAL n_texts * 2048 (src/calibration.py:141), mirrors the
+    symmetric matrices and returns the reference's five lists; non-owners hold None for a layer."""
+
+    def __init__(self, adapter: ModelAdapter, target_layers: list[int] | None = None):
+        import contextlib
+
+        self.adapter = adapter
+        model = adapter.model
+        self.n_layers = adapter.n_layers
+        blocks = adapter.get_transformer_blocks()
+        self.targets = list(target_layers) if target_layers else list(range(self.n_layers))
+        self.device = next(model.parameters()).device
+        n_inner, d = adapter.get_n_inner(), adapter.d_model
+        H, KV, hd = adapter.n_heads, adapter.n_kv_heads, adapter.head_dim
+        f32 = dict(dtype=torch.float32, device=self.device)
+        L = self.n_layers
+        self.cov_mlp, self.cov_q, self.cov_k, self.cov_x = [None] * L, [None] * L, [None] * L, [None] * L
+        for i in self.targets:
+            self.cov_mlp[i] = torch.zeros(n_inner, n_inner, **f32)
+            self.cov_q[i] = torch.zeros(H, hd, hd, **f32)
+            self.cov_k[i] = torch.zeros(KV, hd, hd, **f32)
+            self.cov_x[i] = torch.zeros(d, d, **f32)
+        self.handles: list = []
+        for i in self.targets:
+            adapter.register_hooks(i, blocks[i], cov_mlp_list=self.cov_mlp, cov_q_list=self.cov_q,
+                                   cov_k_list=self.cov_k, cov_x_list=self.cov_x, handles=self.handles,
+                                   logger=logger)
+            self.handles.append(blocks[i].register_forward_hook(self._layer_done(i)))
+        self.bi_batch = torch.zeros(L, dtype=torch.float64, device=self.device)
+        self.bi_total = torch.zeros(L, dtype=torch.float64, device=self.device)
+        adapter.register_bi_hooks(self.bi_batch, self.handles)
+        model.eval()
+        # the LM head is not on the statistics path: run the decoder stack only (its final norm,
+        # whose output closes the last Block-Influence pair, is part of it)
+        self.body = getattr(model, "model", model)
+        self.n_texts = 0
+        self._armed = False
+        self._submitted: set[int] = set()
+        self._mine: dict[int, bool] = {}
+        self.reducer = D.LayerReducer()
+        self._stack = contextlib.ExitStack()
+        if not adapter.config.eager_forward:
+            self._stack.enter_context(fused_elementwise(model))
+
+    def _submit(self, i: int) -> None:
+        if i not in self._submitted:
+            self._submitted.add(i)
+            self._mine[i] = self.reducer.submit(i, self.cov_mlp[i], self.cov_x[i], self.cov_q[i],
+                                                self.cov_k[i])
+
+    def _layer_done(self, i: int):
+        def hook(_mod, _inp, _out):
+            if self._armed:
+                self._submit(i)
+        return hook
+
+    @torch.no_grad()
+    def run_batch(self, batch: torch.Tensor, last: bool = False) -> None:
+        if self._submitted:
+            raise RuntimeError("Calibrator: a batch after the armed (last) one would be lost")
+        self._armed = bool(last)
+        batch = batch.to(self.device, non_blocking=True)
+        self.n_texts += len(batch)
+        self.body(batch, use_cache=False)
+        # sum over the batch, mean over positions (src/calibration.py:122-124)
+        self.bi_total += self.bi_batch / batch.shape[1]
+        self.bi_batch.zero_()
+        self._armed = False
+
+    def close(self) -> None:
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+        self._stack.close()
+
+    @torch.no_grad()
+    def finish(self):
+        self.close()
+        for i in self.targets:          # layers not exchanged during the last batch
+            self._submit(i)
+        self.reducer.wait()
+        count = torch.tensor([float(self.n_texts)], dtype=torch.float64, device=self.device)
+        D.all_reduce_sum_(count)
+        D.all_reduce_sum_(self.bi_total)
+        n_texts_global = int(count.item())
+        bi_scores = (self.bi_total / n_texts_global).tolist()
+        self.adapter.bi_scores = bi_scores
+        scale = 1.0 / float(n_texts_global * NORMALISER_SEQ_LEN)
+        for i in self.targets:
+            if not self._mine[i]:       # only the owner decomposes layer i
+                self.cov_mlp[i] = self.cov_q[i] = self.cov_k[i] = self.cov_x[i] = None
+                continue
+            ops.finalize_sym_(self.cov_mlp[i], scale)
+            ops.finalize_sym_(self.cov_x[i], scale)
+            ops.scale_(self.cov_q[i], scale)
+            ops.scale_(self.cov_k[i], scale)
+        return self.cov_mlp, self.cov_q, self.cov_k, self.cov_x, bi_scores
+
+
 @torch.no_grad()
 def _calibrate_model(adapter: ModelAdapter, n_samples: int, batch_size: int,
                      target_layers: list[int], dataset: str = "wikitext"):
     model = adapter.model
-    n_layers = adapter.n_layers
-    blocks = adapter.get_transformer_blocks()
-    if not target_layers:
-        target_layers = list(range(n_layers))
-    device = next(model.parameters()).device
-
     if adapter.calibs is None:
         from .eval import load_calibration_texts
 
@@ -47,72 +153,17 @@ def _calibrate_model(adapter: ModelAdapter, n_samples: int, batch_size: int,
                                                 dataset=dataset, seq_len=adapter.config.seq_len,
                                                 seed=adapter.config.seed)
     logger.info(f"Detected architecture: {adapter.arch}")
-    logger.info(f"target_layers = {target_layers}")
-
-    n_inner, d = adapter.get_n_inner(), adapter.d_model
-    H, KV, hd = adapter.n_heads, adapter.n_kv_heads, adapter.head_dim
-    f32 = dict(dtype=torch.float32, device=device)
-    cov_mlp = [None] * n_layers
-    cov_q = [None] * n_layers
-    cov_k = [None] * n_layers
-    cov_x = [None] * n_layers
-    for i in target_layers:
-        cov_mlp[i] = torch.zeros(n_inner, n_inner, **f32)
-        cov_q[i] = torch.zeros(H, hd, hd, **f32)
-        cov_k[i] = torch.zeros(KV, hd, hd, **f32)
-        cov_x[i] = torch.zeros(d, d, **f32)
-
-    handles: list = []
-    for i in target_layers:
-        adapter.register_hooks(i, blocks[i], cov_mlp_list=cov_mlp, cov_q_list=cov_q,
-                               cov_k_list=cov_k, cov_x_list=cov_x, handles=handles, logger=logger)
-    bi_batch = torch.zeros(n_layers, dtype=torch.float64, device=device)
-    bi_total = torch.zeros(n_layers, dtype=torch.float64, device=device)
-    adapter.register_bi_hooks(bi_batch, handles)
-
-    model.eval()
-    # the LM head is not on the statistics path: run the decoder stack only (its final norm, whose
-    # output closes the last Block-Influence pair, is part of it)
-    body = getattr(model, "model", model)
-    n_texts = 0
-    import contextlib
-
-    fuse = contextlib.nullcontext() if adapter.config.eager_forward else fused_elementwise(model)
+    logger.info(f"target_layers = {target_layers or list(range(adapter.n_layers))}")
+    cal = Calibrator(adapter, target_layers)
     try:
-        with fuse:
-            for batch in D.shard_batches(adapter.calibs):
-                batch = batch.to(device, non_blocking=True)
-                n_texts += len(batch)
-                body(batch, use_cache=False)
-                # sum over the batch, mean over positions (src/calibration.py:122-124)
-                bi_total += bi_batch / batch.shape[1]
-                bi_batch.zero_()
+        mine = D.shard_batches(adapter.calibs)
+        for i, batch in enumerate(mine):
+            cal.run_batch(batch, last=(i == len(mine) - 1))
+        out = cal.finish()
     finally:
-        for h in handles:
-            h.remove()
-
-    # ---- cross-rank exchange: one reduction per statistic per layer, to the layer's owner
-    count = torch.tensor([float(n_texts)], dtype=torch.float64, device=device)
-    D.all_reduce_sum_(count)
-    D.all_reduce_sum_(bi_total)
-    n_texts_global = int(count.item())
-    bi_scores = (bi_total / n_texts_global).tolist()
-    adapter.bi_scores = bi_scores
-
-    scale = 1.0 / float(n_texts_global * NORMALISER_SEQ_LEN)
-    for i in target_layers:
-        mine = True
-        for lst in (cov_mlp, cov_x, cov_q, cov_k):
-            mine = D.reduce_to_owner(lst[i], i)
-        if not mine:
-            cov_mlp[i] = cov_q[i] = cov_k[i] = cov_x[i] = None   # only the owner decomposes layer i
-            continue
-        ops.finalize_sym_(cov_mlp[i], scale)
-        ops.finalize_sym_(cov_x[i], scale)
-        ops.scale_(cov_q[i], scale)
-        ops.scale_(cov_k[i], scale)
+        cal.close()
     logger.info("Finished calibration and computed BI scores.")
-    return cov_mlp, cov_q, cov_k, cov_x, bi_scores
+    return out
 
 
 # ================================================================================================
@@ -143,6 +194,13 @@ class _LayerStepper:
             raise NotImplementedError("layer-streamed calibration needs a Llama/Qwen3-style decoder")
         if any(t != "full_attention" for t in (getattr(model.config, "layer_types", None) or [])):
             raise NotImplementedError("layer-streamed calibration supports full-attention layers only")
+        # the layers are called with attention_mask=None: sdpa / flash kernels are then causal
+        # (is_causal), HF's eager attention would be BIDIRECTIONAL and silently change C and BI
+        impl = getattr(model.config, "_attn_implementation", None) or "sdpa"
+        if impl not in ("sdpa", "flash_attention_2", "flash_attention_3"):
+            raise NotImplementedError(
+                f"layer-streamed calibration needs attn_implementation sdpa or flash_attention_* "
+                f"(got {impl!r}: without an explicit mask it would not be causal)")
         self.device = next(model.parameters()).device
         if adapter.calibs is None:
             from .eval import load_calibration_texts
@@ -215,6 +273,7 @@ def iter_layer_statistics(adapter: ModelAdapter, target_layers: list[int] | None
     count = torch.tensor([float(st.n_texts)], dtype=torch.float64, device=st.device)
     D.all_reduce_sum_(count)
     scale = 1.0 / float(int(count.item()) * NORMALISER_SEQ_LEN)
+    reducer = D.LayerReducer()
     for l in range(L):
         handles: list = []
         cov = None
@@ -235,9 +294,8 @@ def iter_layer_statistics(adapter: ModelAdapter, target_layers: list[int] | None
                 h.remove()
         if cov is None:
             continue
-        mine = True
-        for lst in cov:
-            mine = D.reduce_to_owner(lst[l], l)
+        mine = reducer.submit(l, cov[0][l], cov[3][l], cov[1][l], cov[2][l])
+        reducer.wait()
         if not mine:
             del cov
             yield l, None, None, None, None

@@ -69,53 +69,8 @@ def _compress_layer(adapter: ModelAdapter, cov, keep_ratios, layer_idx: int) -> 
 @torch.no_grad()
 def compress_nystrom(adapter: ModelAdapter, cov, keep_ratios, target_layers, ridge_lambda=1e-4):
     """Layer loop + `save_layer(suffix="mlp")` (compress_mlp.py:67-117).  As in the reference the
-    ridge actually used is `adapter.config.nystrom_ridge` (:93).
-
-    Layers are independent: with `config.mlp_workers` > 1 that many host threads, each with its
-    own CUDA stream (and, inside the library, its own set of lanes), take layers from a shared
-    list so several factorisations overlap.  Results do not depend on the number of workers.
-    Default 1: on Llama-2-7B two workers measured 22.2 vs 21.8 ms/layer.  The host is not the
-    limit (a factorisation is enqueued in 3.5 ms and runs for 10 ms); the persistent bulk GEMMs of
-    one factorisation already hold most SMs, so a second chain queues behind them."""
-    layers = list(D.owned_layers(target_layers))
-    workers = max(1, min(int(getattr(adapter.config, "mlp_workers", 1)), len(layers)))
-    if workers == 1 or not torch.cuda.is_available():
-        for layer_idx in layers:
-            _compress_layer(adapter, cov, keep_ratios, layer_idx)
-        return
-
-    import threading
-
-    adapter.prepare_writer()                # created once, before the workers race for it
-    device = cov[layers[0]].device
-    caller = torch.cuda.current_stream(device)
-    ready = torch.cuda.Event()
-    ready.record(caller)
-    pending = list(reversed(layers))        # pop() hands layers out in ascending order
-    lock = threading.Lock()
-    errors: list[BaseException] = []
-    streams = [torch.cuda.Stream(device=device) for _ in range(workers)]
-
-    def work(stream):
-        try:
-            torch.cuda.set_device(device)
-            with torch.no_grad(), torch.cuda.stream(stream):
-                stream.wait_event(ready)     # statistics / weights produced on the caller's stream
-                while not errors:
-                    with lock:
-                        if not pending:
-                            break
-                        layer_idx = pending.pop()
-                    _compress_layer(adapter, cov, keep_ratios, layer_idx)
-        except BaseException as e:           # re-raised on the calling thread
-            errors.append(e)
-
-    threads = [threading.Thread(target=work, args=(s,), name=f"mg-mlp-{i}") for i, s in enumerate(streams)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    for s in streams:
-        caller.wait_stream(s)
-    if errors:
-        raise errors[0]
+    ridge actually used is `adapter.config.nystrom_ridge` (:93).  Each rank takes the layers it
+    owns (`distributed.owned_layers`); inside a layer the library spreads the factorisation over
+    its own lanes, so one host thread keeps the GPU busy."""
+    for layer_idx in D.owned_layers(target_layers):
+        _compress_layer(adapter, cov, keep_ratios, layer_idx)

@@ -3,8 +3,13 @@
 The reference forms sqrt(C_x) by a d x d eigendecomposition, inverts it by LU and runs one (GQA)
 or two (MHA, the second one FULL d x d) SVDs per head.  Algebraically the new heads are hd x r
 recombinations of the old ones determined by hd x hd symmetric eigenproblems (SURVEY §3.5,
-Appendix B4/B5); `mg_vo_compress` builds those Gram matrices on the tensor cores, solves the
-eigenproblems with a batched fp64 Jacobi in shared memory and applies the recombination.
+Appendix B4/B5): the right singular pairs of sqrt(C) W_v,h^T are the eigenpairs of
+G1[h] = W_v,h (C_x + ridge I) W_v,h^T.  `mg_vo_compress` forms P = (C_x + ridge I) W_v^T on the
+tensor cores, accumulates the hd x hd Grams W_v,h P_h in FP64 (the fp32 tensor-core accumulator
+would lose 2^-24 of the largest eigenvalue, which is what the small singular values divide by),
+solves the eigenproblems with a batched fp64 Jacobi in shared memory and applies the recombination.
+(`method=VO_FACTOR` goes through the blocked Cholesky factor of C_x + ridge I instead; measured
+equally accurate up to cond(G1) = 3e5 and 3x slower, so it is not the default.)
 Singular vectors are defined up to sign, so V' / O' match the reference up to a per-component
 sign; the products O'V' match.
 """
@@ -88,12 +93,12 @@ def _prepare_layer(adapter, cov, keep_ratios, layer, H, KV, hd):
     if got is None:
         return None
     rank_i, comps, wv, wo = got
-    ws = ops.vo_prepare(cov[layer], adapter.config.ridge_vo, wv, wo, H, KV, hd)
-    return layer, rank_i, comps, wv, wo, ws, ops.vo_outputs(wv, H, KV, rank_i)
+    ws, info = ops.vo_prepare(cov[layer], adapter.config.ridge_vo, wv, wo, H, KV, hd)
+    return layer, rank_i, comps, wv, wo, ws, ops.vo_outputs(wv, H, KV, rank_i), info
 
 
 def _finish_layer(adapter, item, H, KV, hd):
-    layer, rank_i, comps, wv, wo, ws, out = item
+    layer, rank_i, comps, wv, wo, ws, out, _ = item
     here = torch.cuda.current_stream(ws.device)
     for t in (ws, *out):                                     # allocated on the caller's stream
         t.record_stream(here)

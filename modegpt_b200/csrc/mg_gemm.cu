@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "mg_once.cuh"
 #include "mg_ptx.cuh"
 
 namespace mg {
@@ -672,13 +673,12 @@ template <int BN>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                 const KParams& kp, int cta_cap, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes);
-    if (e != cudaSuccess) return -1000 - static_cast<int>(e);
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (int rc = once.run([] {
+        return cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::smem_bytes);
+      }))
+    return rc;
   const int grid = kp.total_work < cta_cap ? kp.total_work : cta_cap;
   gemm_tn_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, tmD, kp);
   cudaError_t e = cudaGetLastError();
@@ -803,13 +803,12 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
     kp.tma_epi = 1;
   }
   if (pair) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tn_pair_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
-      if (e != cudaSuccess) return -1000 - static_cast<int>(e);
-      attr_set = true;
-    }
+    static PerDeviceOnce once;
+    if (int orc = once.run([] {
+          return cudaFuncSetAttribute(gemm_tn_pair_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+        }))
+      return orc;
     const int max_clusters = cta_cap / 2;
     const int clusters = kp.total_work < max_clusters ? kp.total_work : max_clusters;
     gemm_tn_pair_kernel<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(tmA, tmB, tmD, kp);

@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "mg_gemm.cuh"
+#include "mg_once.cuh"
 #include "mg_prof.cuh"
 #include "mg_ptx.cuh"
 
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ dst,
                                                            int64_t ld_dst, int64_t plane_stride,
                                                            float* __restrict__ colsumsq,
-                                                           float diag_add) {
+                                                           float diag_add, int upper_only) {
   __shared__ __nv_bfloat16 tile[kPlanes][64][34];
   __shared__ float csum[4][64];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     const int rr = ty + 4 * i;
     const int64_t r = r0 + rr;
     float x = 0.f;
-    if (r < rows && c < cols) x = src[r * ld_src + c] + (r == c ? diag_add : 0.f);
+    if (r < rows && c < cols && (!upper_only || c >= r))
+      x = src[r * ld_src + c] + (r == c ? diag_add : 0.f);
     acc = fmaf(x, x, acc);
     __nv_bfloat16 h, m, l;
     split3(x, h, m, l);
@@ -466,27 +468,26 @@ __global__ void __launch_bounds__(kTrsmThreads, 2)
 
 int split_planes(const float* src, int64_t ld_src, int64_t rows, int64_t cols, __nv_bfloat16* dst,
                  int64_t ld_dst, int64_t plane_stride, bool transpose, float* colsumsq,
-                 cudaStream_t s, float diag_add) {
+                 cudaStream_t s, float diag_add, bool upper_only) {
   if (rows <= 0 || cols <= 0) return 0;
   dim3 grid(static_cast<unsigned>((cols + 63) / 64), static_cast<unsigned>((rows + 31) / 32));
   if (transpose)
     split_planes_kernel<true><<<grid, 256, 0, s>>>(src, ld_src, rows, cols, dst, ld_dst,
-                                                   plane_stride, colsumsq, diag_add);
+                                                   plane_stride, colsumsq, diag_add, upper_only);
   else
     split_planes_kernel<false><<<grid, 256, 0, s>>>(src, ld_src, rows, cols, dst, ld_dst,
-                                                    plane_stride, colsumsq, diag_add);
+                                                    plane_stride, colsumsq, diag_add, upper_only);
   return cuda_rc();
 }
 
 int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bwd, int* info,
              cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kPotrfSmem));
-    if (e != cudaSuccess) return -1000 - static_cast<int>(e);
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (int rc = once.run([] {
+        return cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kPotrfSmem));
+      }))
+    return rc;
   potrf128_kernel<<<1, kPotrfThreads, kPotrfSmem, s>>>(A, ld, j0, nb, t_fwd, t_bwd, info);
   return cuda_rc();
 }
@@ -496,13 +497,12 @@ int trsm128(const float* tblock, bool reversed, int nb, const float* B, int64_t 
             __nv_bfloat16* tplanes, int64_t ldtp, int64_t tpstride, float* colsumsq,
             cudaStream_t s) {
   if (ncols <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kTrsmSmem));
-    if (e != cudaSuccess) return -1000 - static_cast<int>(e);
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (int rc = once.run([] {
+        return cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kTrsmSmem));
+      }))
+    return rc;
   const unsigned grid = static_cast<unsigned>((ncols + kTrsmCols - 1) / kTrsmCols);
   trsm128_kernel<<<grid, kTrsmThreads, kTrsmSmem, s>>>(tblock, reversed ? 1 : 0, nb, B, ldb, ncols,
                                                        alpha, X, ldx, planes, ldp, pstride, tplanes,

@@ -18,10 +18,12 @@ constexpr int kTBlock = kNB * kTLd;
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // dst_p[r, c] (or dst_p[c, r] when transpose) = p-th bf16 plane of src[r, c];
-// optional colsumsq[c] += sum_r src[r, c]^2; diag_add is added to src[i, i] before splitting.
+// optional colsumsq[c] += sum_r src[r, c]^2; diag_add is added to src[i, i] before splitting;
+// upper_only treats src[r, c] with c < r as zero (the strict lower triangle of an in-place
+// Cholesky factor is scratch).
 int split_planes(const float* src, int64_t ld_src, int64_t rows, int64_t cols, __nv_bfloat16* dst,
                  int64_t ld_dst, int64_t plane_stride, bool transpose, float* colsumsq,
-                 cudaStream_t s, float diag_add = 0.f);
+                 cudaStream_t s, float diag_add = 0.f, bool upper_only = false);
 
 // Cholesky of the nb x nb (nb <= 128) diagonal block at (j0, j0) of the fp32 matrix A: upper
 // factor U11 written back in place (upper triangle), fp64 arithmetic, hierarchical 32-blocking

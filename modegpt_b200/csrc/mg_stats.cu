@@ -112,6 +112,26 @@ __global__ void __launch_bounds__(256) finalize_sym_kernel(float* __restrict__ C
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed upper triangle (row-major, row i holds columns i..n-1 at offset i*n - i*(i-1)/2): the
+// wire format of the cross-rank reduction — half the bytes of the square accumulator.
+// One block row per matrix row; within a row both sides are contiguous, so loads and stores are
+// full 128-byte lines apart from the ragged ends.
+// ---------------------------------------------------------------------------------------------
+template <bool PACK>
+__global__ void __launch_bounds__(256) pack_upper_kernel(float* __restrict__ C, int64_t n,
+                                                         int64_t ldc, float* __restrict__ packed) {
+  for (int64_t r = blockIdx.y; r < n; r += gridDim.y) {
+    float* row = C + r * ldc;
+    float* prow = packed + (r * n - r * (r - 1) / 2) - r;   // prow[c] is element (r, c), c >= r
+    for (int64_t c = r + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < n;
+         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      if (PACK) prow[c] = row[c];
+      else row[c] = prow[c];
+    }
+  }
+}
+
 __global__ void scale_kernel(float* __restrict__ x, int64_t count, float scale) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
@@ -209,6 +229,28 @@ int mg_finalize_sym_f32(float* C, int64_t n, int64_t ldc, float scale, void* str
   const int nb = static_cast<int>((n + 31) / 32);
   finalize_sym_kernel<<<dim3(nb, nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(C, n, ldc,
                                                                                     scale);
+  return cuda_rc();
+}
+
+int mg_pack_upper_f32(const float* C, int64_t n, int64_t ldc, float* packed, void* stream) {
+  if (!C || !packed) return -1;
+  if (n <= 0) return -2;
+  if (ldc < n) return -7;
+  const unsigned gx = static_cast<unsigned>(n >= 4096 ? 4 : 1);
+  const unsigned gy = static_cast<unsigned>(n < 65535 ? n : 65535);
+  pack_upper_kernel<true><<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      const_cast<float*>(C), n, ldc, packed);
+  return cuda_rc();
+}
+
+int mg_unpack_upper_f32(const float* packed, int64_t n, float* C, int64_t ldc, void* stream) {
+  if (!C || !packed) return -1;
+  if (n <= 0) return -2;
+  if (ldc < n) return -7;
+  const unsigned gx = static_cast<unsigned>(n >= 4096 ? 4 : 1);
+  const unsigned gy = static_cast<unsigned>(n < 65535 ? n : 65535);
+  pack_upper_kernel<false><<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      C, n, ldc, const_cast<float*>(packed));
   return cuda_rc();
 }
 

@@ -18,6 +18,7 @@
 #include "../../include/modegpt_b200.h"
 #include "mg_gemm.cuh"
 #include "mg_linalg.cuh"
+#include "mg_once.cuh"
 
 namespace {
 
@@ -294,24 +295,134 @@ __device__ void jacobi_eig(EigSmem& s, int hd) {
   __syncthreads();
 }
 
+// G[a, b] = sum_c X(a, c) * Y(b, c) in fp64 for one head and one slab of the reduction index:
+// X(a, c) = X[head * xh + a * xsa + c * xsc] (likewise Y).  The fp32 tensor-core accumulators lose
+// ~2^-24 of the LARGEST eigenvalue, which is what limits the small singular values the type-III
+// factors divide by; the hd x hd Grams are therefore accumulated in fp64 on the CUDA cores
+// (2 * d * hd^2 flop per head: 4.3 GFLOP for a 7B layer).  Partial sums per slab are written to
+// out[head][slab][hd * hd] and added in a fixed order by the consumer (no atomics: results do not
+// depend on timing).
+constexpr int kGramKC = 32;   // reduction indices per shared-memory tile
+template <class TX, class TY>
+__global__ void __launch_bounds__(256)
+    gram64_kernel(const TX* __restrict__ X, int64_t xh, int64_t xsa, int64_t xsc,
+                  const TY* __restrict__ Y, int64_t yh, int64_t ysa, int64_t ysc, int same, int hd,
+                  int64_t K, int64_t slab, double* __restrict__ out) {
+  extern __shared__ __align__(16) double gsm[];
+  double* xs = gsm;                              // [kGramKC][128]
+  double* ys = same ? gsm : gsm + kGramKC * kMaxHd;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int head = blockIdx.x, part = blockIdx.y, nparts = gridDim.y;
+  const TX* x = X + static_cast<int64_t>(head) * xh;
+  const TY* y = Y + static_cast<int64_t>(head) * yh;
+  const int64_t c_begin = static_cast<int64_t>(part) * slab;
+  const int64_t c_end = c_begin + slab < K ? c_begin + slab : K;
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += kGramKC) {
+    __syncthreads();
+    // the fastest-varying thread index follows the contiguous direction of the operand
+    for (int e = t; e < kGramKC * kMaxHd; e += 256) {
+      int a, kk;
+      if (xsc == 1) {
+        kk = e & (kGramKC - 1);
+        a = e / kGramKC;
+      } else {
+        a = e & (kMaxHd - 1);
+        kk = e / kMaxHd;
+      }
+      const int64_t c = c0 + kk;
+      xs[kk * kMaxHd + a] =
+          (a < hd && c < c_end) ? static_cast<double>(static_cast<float>(x[a * xsa + c * xsc])) : 0.0;
+    }
+    if (!same) {
+      for (int e = t; e < kGramKC * kMaxHd; e += 256) {
+        int a, kk;
+        if (ysc == 1) {
+          kk = e & (kGramKC - 1);
+          a = e / kGramKC;
+        } else {
+          a = e & (kMaxHd - 1);
+          kk = e / kMaxHd;
+        }
+        const int64_t c = c0 + kk;
+        ys[kk * kMaxHd + a] =
+            (a < hd && c < c_end) ? static_cast<double>(static_cast<float>(y[a * ysa + c * ysc])) : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < kGramKC; ++kk) {
+      double xa[8], yb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xa[i] = xs[kk * kMaxHd + ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) yb[j] = ys[kk * kMaxHd + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(xa[i], yb[j], acc[i][j]);
+    }
+  }
+  double* o = out + (static_cast<int64_t>(head) * nparts + part) * hd * hd;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int a = ty + 16 * i;
+    if (a >= hd) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = tx + 16 * j;
+      if (b < hd) o[a * hd + b] = acc[i][j];
+    }
+  }
+}
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<double>(in[i]);
+}
+
+// dst (upper triangle, ld = ldd) = src + ridge * I
+__global__ void copy_upper_ridge_kernel(const float* __restrict__ src, int64_t lds,
+                                        float* __restrict__ dst, int64_t ldd, int64_t n, float ridge) {
+  const int64_t r = blockIdx.y;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < n;
+       c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (c >= r) dst[r * ldd + c] = src[r * lds + c] + (c == r ? ridge : 0.f);
+  }
+}
+
 // One CTA per kv head.
-//   G1 [KV, hd, hd] fp32, G2 [H, hd, hd] fp32 (MHA only, may be null), scratch [KV][2][hd*hd] fp32,
-//   Rv, Ro [KV][hd, r] fp32.
+//   G1 [KV][n1][hd*hd] fp64 partial sums, G2 [H][n2][hd*hd] fp64 (MHA only, may be null),
+//   scratch [KV][2][hd*hd] fp32, Rv, Ro [KV][hd, r] fp32.
 __global__ void __launch_bounds__(1024, 1)
-    vo_factor_kernel(const float* __restrict__ G1, const float* __restrict__ G2, int hd, int r,
-                     float* __restrict__ scratch, float* __restrict__ Rv, float* __restrict__ Ro) {
+    vo_factor_kernel(const double* __restrict__ G1, int n1, const double* __restrict__ G2, int n2,
+                     int hd, int r, float* __restrict__ scratch, float* __restrict__ Rv,
+                     float* __restrict__ Ro) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EigSmem s = carve_eig(smem_raw, hd);
   const int t = threadIdx.x, nt = blockDim.x;
   const int ld = hd + 1, ldv = hd + 4;
   const int h = blockIdx.x;
-  const float* g1 = G1 + static_cast<int64_t>(h) * hd * hd;
+  const int hh = hd * hd;
+  const double* g1 = G1 + static_cast<int64_t>(h) * n1 * hh;
   float* rv = Rv + static_cast<int64_t>(h) * hd * r;
   float* ro = Ro + static_cast<int64_t>(h) * hd * r;
 
-  for (int e = t; e < hd * hd; e += nt) {
+  for (int e = t; e < hh; e += nt) {
     const int i = e / hd, k = e - i * hd;
-    s.g[i * ld + k] = 0.5 * (static_cast<double>(g1[i * hd + k]) + static_cast<double>(g1[k * hd + i]));
+    double x = 0.0, y = 0.0;
+    for (int p = 0; p < n1; ++p) {
+      x += g1[p * hh + i * hd + k];
+      y += g1[p * hh + k * hd + i];
+    }
+    // a failed factorisation (reported through *info by mg_vo_prepare) leaves NaNs behind: keep
+    // the eigensolver's index arithmetic well defined, the caller discards the result anyway
+    const double gsym = 0.5 * (x + y);
+    s.g[i * ld + k] = isfinite(gsym) ? gsym : 0.0;
   }
   __syncthreads();
   jacobi_eig(s, hd);
@@ -330,42 +441,63 @@ __global__ void __launch_bounds__(1024, 1)
   }
 
   // ---- MHA second stage
-  const float* g2 = G2 + static_cast<int64_t>(h) * hd * hd;
-  float* vg = scratch + static_cast<int64_t>(h) * 2 * hd * hd;  // V (sorted columns)
-  float* tg = vg + hd * hd;                                     // T = G2 * D
+  const double* g2 = G2 + static_cast<int64_t>(h) * n2 * hh;
+  float* vg = scratch + static_cast<int64_t>(h) * 2 * hh;       // V (sorted columns)
   double* sval = s.cs;  // singular values S (sorted), reuse the rotation buffer
   if (t < hd) sval[t] = sqrt(fmax(s.lam[s.perm[t]], 0.0));
-  for (int e = t; e < hd * hd; e += nt) {
+  for (int e = t; e < hh; e += nt) {
     const int i = e / hd, a = e - i * hd;
     vg[e] = s.v[i * ldv + s.perm[a]];
   }
   __syncthreads();
   // D = V S in shared memory (overwrites v, sorted order)
-  for (int e = t; e < hd * hd; e += nt) {
+  for (int e = t; e < hh; e += nt) {
     const int i = e / hd, a = e - i * hd;
     s.v[i * ldv + a] = static_cast<float>(static_cast<double>(vg[e]) * sval[a]);
   }
   __syncthreads();
-  // T = G2 D
-  for (int e = t; e < hd * hd; e += nt) {
+  // T = G2 D   (fp64, kept in the fp64 buffer: s.g is free until B is formed)
+  for (int e = t; e < hh; e += nt) {
     const int i = e / hd, a = e - i * hd;
     double acc = 0.0;
-    for (int k = 0; k < hd; ++k)
-      acc += 0.5 * (static_cast<double>(g2[i * hd + k]) + static_cast<double>(g2[k * hd + i])) *
-             static_cast<double>(s.v[k * ldv + a]);
-    tg[e] = static_cast<float>(acc);
+    for (int k = 0; k < hd; ++k) {
+      double x = 0.0, y = 0.0;
+      for (int p = 0; p < n2; ++p) {
+        x += g2[p * hh + i * hd + k];
+        y += g2[p * hh + k * hd + i];
+      }
+      acc += 0.5 * (x + y) * static_cast<double>(s.v[k * ldv + a]);
+    }
+    s.g[i * ld + a] = acc;
   }
   __syncthreads();
-  // B = D^T T  (symmetric), into the fp64 buffer
-  for (int e = t; e < hd * hd; e += nt) {
-    const int a = e / hd, b = e - a * hd;
-    double acc = 0.0;
-    for (int k = 0; k < hd; ++k)
-      acc += static_cast<double>(s.v[k * ldv + a]) * static_cast<double>(tg[k * hd + b]);
-    s.g[a * ld + b] = acc;
+  // B = D^T T  (symmetric): computed into registers first (s.g holds T), then written back
+  {
+    constexpr int kPer = kMaxHd * kMaxHd / 1024;   // elements per thread at hd = 128
+    double bacc[kPer];
+#pragma unroll
+    for (int c = 0; c < kPer; ++c) {
+      const int e = t + c * nt;
+      double acc = 0.0;
+      if (e < hh) {
+        const int a = e / hd, b = e - a * hd;
+        for (int k = 0; k < hd; ++k)
+          acc += static_cast<double>(s.v[k * ldv + a]) * s.g[k * ld + b];
+      }
+      bacc[c] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kPer; ++c) {
+      const int e = t + c * nt;
+      if (e < hh) {
+        const int a = e / hd, b = e - a * hd;
+        s.g[a * ld + b] = bacc[c];
+      }
+    }
   }
   __syncthreads();
-  for (int e = t; e < hd * hd; e += nt) {  // symmetrise
+  for (int e = t; e < hh; e += nt) {  // symmetrise
     const int a = e / hd, b = e - a * hd;
     if (a < b) {
       const double x = 0.5 * (s.g[a * ld + b] + s.g[b * ld + a]);
@@ -373,32 +505,53 @@ __global__ void __launch_bounds__(1024, 1)
       s.g[b * ld + a] = x;
     }
   }
-  // keep S: jacobi_eig overwrites cs; stash S in red-free space = lam after copying
+  // keep S: jacobi_eig overwrites cs
   __shared__ double s_keep[kMaxHd];
   if (t < hd) s_keep[t] = sval[t];
   __syncthreads();
   jacobi_eig(s, hd);  // s.v now holds U_p (unsorted columns), perm the descending order
-  // Rv = V S^-1 U_p[:, :r],  Ro = V S U_p[:, :r]
+  // Ro = V S U_p[:, :r].  Rv = V S^-1 U_p[:, :r] is NOT formed by dividing: the components of the
+  // leading eigenvectors u_a along the small singular directions are tiny (~sigma_k / sigma_1) and
+  // carry only the eigensolver's absolute accuracy, so sigma_k^-1 u_a[k] would amplify its
+  // rounding by sigma_1 / sigma_k.  From B u = lambda u with B = S M S, M = V^T G2 V:
+  //     S^-1 u = M (S u) / lambda     =>     Rv = V S^-1 U_r = G2 (V S U_r) Lambda_r^-1 = G2 Ro Lambda_r^-1,
+  // which only ever divides by the r LARGEST eigenvalues of B.
   for (int e = t; e < hd * r; e += nt) {
     const int i = e / r, a = e - i * r;
     const int col = s.perm[a];
-    double av = 0.0, ao = 0.0;
-    for (int k = 0; k < hd; ++k) {
-      const double v = vg[i * hd + k];
-      const double up = s.v[k * ldv + col];
-      const double sv = s_keep[k];
-      av += v / fmax(sv, 1e-30) * up;
-      ao += v * sv * up;
-    }
-    rv[e] = static_cast<float>(av);
+    double ao = 0.0;
+    for (int k = 0; k < hd; ++k)
+      ao += static_cast<double>(vg[i * hd + k]) * s_keep[k] * static_cast<double>(s.v[k * ldv + col]);
     ro[e] = static_cast<float>(ao);
+  }
+  __syncthreads();     // ro (global, written by this CTA) is read back below
+  for (int e = t; e < hd * r; e += nt) {
+    const int i = e / r, a = e - i * r;
+    const double lam_a = s.lam[s.perm[a]];
+    double av = 0.0;
+    for (int j = 0; j < hd; ++j) {
+      double x = 0.0, y = 0.0;
+      for (int p = 0; p < n2; ++p) {
+        x += g2[p * hh + i * hd + j];
+        y += g2[p * hh + j * hd + i];
+      }
+      av += 0.5 * (x + y) * static_cast<double>(ro[j * r + a]);
+    }
+    rv[e] = lam_a > 0.0 ? static_cast<float>(av / lam_a) : 0.f;
   }
 }
 
-// V'[h*r + a, c] = sum_k Rv[h][k, a] * Wv[h*hd + k, c]
+template <class OUT>
+__device__ __forceinline__ OUT to_out(float x);
+template <>
+__device__ __forceinline__ bf16 to_out<bf16>(float x) { return __float2bfloat16_rn(x); }
+template <>
+__device__ __forceinline__ float to_out<float>(float x) { return x; }
+
+template <class OUT>
 __global__ void __launch_bounds__(256) vo_apply_v_kernel(const bf16* __restrict__ Wv, int64_t ldwv,
                                                          const float* __restrict__ Rv, int hd,
-                                                         int r, int64_t d, bf16* __restrict__ out,
+                                                         int r, int64_t d, OUT* __restrict__ out,
                                                          int64_t ldo) {
   extern __shared__ float sh[];  // Rv[h]: [hd][r]
   const int h = blockIdx.y;
@@ -425,15 +578,16 @@ __global__ void __launch_bounds__(256) vo_apply_v_kernel(const bf16* __restrict_
 #pragma unroll
   for (int i = 0; i < kMaxA; ++i) {
     const int a = ay + 4 * i;
-    if (a < r) out[(static_cast<int64_t>(h) * r + a) * ldo + c] = __float2bfloat16_rn(acc[i]);
+    if (a < r) out[(static_cast<int64_t>(h) * r + a) * ldo + c] = to_out<OUT>(acc[i]);
   }
 }
 
 // O'[c, q*r + a] = sum_k Wo[c, q*hd + k] * Ro[q / group][k, a]
+template <class OUT>
 __global__ void __launch_bounds__(256) vo_apply_o_kernel(const bf16* __restrict__ Wo, int64_t ldwo,
                                                          const float* __restrict__ Ro, int group,
                                                          int hd, int r, int64_t d,
-                                                         bf16* __restrict__ out, int64_t ldo) {
+                                                         OUT* __restrict__ out, int64_t ldo) {
   extern __shared__ float sh[];
   float* ro_s = sh;                 // [hd][r]
   float* w_s = sh + hd * r;         // [64][hd + 1]
@@ -457,7 +611,7 @@ __global__ void __launch_bounds__(256) vo_apply_o_kernel(const bf16* __restrict_
     for (int a = ax; a < r; a += nthr_a) {
       float acc = 0.f;
       for (int k = 0; k < hd; ++k) acc = fmaf(w_s[ci * (hd + 1) + k], ro_s[k * r + a], acc);
-      out[c * ldo + static_cast<int64_t>(q) * r + a] = __float2bfloat16_rn(acc);
+      out[c * ldo + static_cast<int64_t>(q) * r + a] = to_out<OUT>(acc);
     }
   }
 }
@@ -480,13 +634,24 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
   }
 }
 
+// ---- workspace ----------------------------------------------------------------------------------
+constexpr int kMaxGramParts = 32;
+
+inline int gram_parts(int heads) {
+  int n = (2 * 148 + heads - 1) / heads;
+  return n < 1 ? 1 : (n > kMaxGramParts ? kMaxGramParts : n);
+}
+
 struct VoWs {
-  bf16* c_planes;   // [3][d x dp]
+  // factor route (method 0): C + rho I = U^T U, M^T = W_v U^T, G1 = M^T M (fp64)
+  float* a;         // [d x dp]       C + rho I (upper) -> U in place
+  mg::CholWorkspace chol;
+  bf16* ut_planes;  // [3][dp x dp]   planes of U^T (lower, zero above); Gram route: planes of C + rho I
   bf16* wvt;        // [d x vp]       W_v^T
-  float* p;         // [d x vp]       (C + rho I) W_v^T
-  bf16* p_planes;   // [3][d x vp]
-  float* g1;        // [KV, hd, hd]
-  float* g2;        // [H, hd, hd]
+  float* mt;        // [vp x dp]      M^T = W_v U^T;  Gram route: P = (C + rho I) W_v^T as [d x vp]
+  double* g1;       // [KV][parts][hd*hd]
+  float* g2f;       // [H, hd, hd]    tensor-core W_o,h^T W_o,h (hd in {32, 64, 128})
+  double* g2;       // [H][parts][hd*hd]
   float* scratch;   // [KV][2][hd*hd]
   float* rv;        // [KV][hd, r<=hd]
   float* ro;
@@ -508,19 +673,48 @@ struct Carver {
 
 VoWs carve_vo(void* ptr, int64_t d, int H, int KV, int hd) {
   const int64_t dp = mg::round_up(d, 64), vp = mg::round_up(static_cast<int64_t>(KV) * hd, 64);
+  const int64_t panels = (d + mg::kNB - 1) / mg::kNB;
+  const size_t hh = static_cast<size_t>(hd) * hd;
   Carver c(ptr);
   VoWs w{};
-  w.c_planes = c.take<bf16>(kPlanes * d * dp);
+  w.a = c.take<float>(d * dp);
+  w.chol.u_planes = c.take<bf16>(kPlanes * dp * dp);
+  w.chol.l_planes = nullptr;
+  w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
+  w.chol.t_bwd = nullptr;
+  w.chol.n_pad = dp;
+  w.ut_planes = c.take<bf16>(kPlanes * dp * dp);
   w.wvt = c.take<bf16>(d * vp);
-  w.p = c.take<float>(d * vp);
-  w.p_planes = c.take<bf16>(kPlanes * d * vp);
-  w.g1 = c.take<float>(static_cast<size_t>(KV) * hd * hd);
-  w.g2 = c.take<float>(static_cast<size_t>(H) * hd * hd);
-  w.scratch = c.take<float>(static_cast<size_t>(KV) * 2 * hd * hd);
-  w.rv = c.take<float>(static_cast<size_t>(KV) * hd * hd);
-  w.ro = c.take<float>(static_cast<size_t>(KV) * hd * hd);
+  w.mt = c.take<float>((vp > d ? vp : d) * (dp > vp ? dp : vp));
+  w.g1 = c.take<double>(static_cast<size_t>(KV) * gram_parts(KV) * hh);
+  w.g2f = c.take<float>(static_cast<size_t>(H) * hh);
+  w.g2 = c.take<double>(static_cast<size_t>(H) * gram_parts(H) * hh);
+  w.scratch = c.take<float>(static_cast<size_t>(KV) * 2 * hh);
+  w.rv = c.take<float>(static_cast<size_t>(KV) * hh);
+  w.ro = c.take<float>(static_cast<size_t>(KV) * hh);
   w.bytes = c.off + 256;
   return w;
+}
+
+inline bool tensor_hd(int hd) { return hd == 32 || hd == 64 || hd == 128; }
+inline bool valid_hd(int hd) { return hd >= 4 && hd <= kMaxHd && hd % 4 == 0; }
+
+template <class TX, class TY>
+int launch_gram64(const TX* X, int64_t xh, int64_t xsa, int64_t xsc, const TY* Y, int64_t yh,
+                  int64_t ysa, int64_t ysc, bool same, int heads, int hd, int64_t K, int parts,
+                  double* out, cudaStream_t s) {
+  static mg::PerDeviceOnce once;
+  const int smem = static_cast<int>(sizeof(double) * kGramKC * kMaxHd * 2);
+  if (int rc = once.run([smem] {
+        return cudaFuncSetAttribute(gram64_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem);
+      }))
+    return rc;
+  int64_t slab = (K + parts - 1) / parts;
+  slab = mg::round_up(slab, kGramKC);
+  gram64_kernel<TX, TY><<<dim3(heads, parts), 256, same ? smem / 2 : smem, s>>>(
+      X, xh, xsa, xsc, Y, yh, ysa, ysc, same ? 1 : 0, hd, K, slab, out);
+  return cuda_rc();
 }
 
 }  // namespace
@@ -547,98 +741,136 @@ size_t mg_vo_ws_bytes(int64_t d, int n_heads, int n_kv_heads, int hd) {
 
 int mg_vo_prepare(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
                   const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
-                  void* ws, size_t ws_bytes, void* stream) {
-  if (!Cx || !Wv || !Wo || !ws) return -1;
+                  int method, int* info, void* ws, size_t ws_bytes, void* stream) {
+  if (!Cx || !Wv || !Wo || !ws || !info) return -1;
   if (d <= 0 || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads) return -2;
-  if (hd != 32 && hd != 64 && hd != 128) return -6;
+  if (!valid_hd(hd)) return -6;
+  if (method != MG_VO_FACTOR && method != MG_VO_GRAM) return -11;
   if (ldc < d || ldwv < d || ldwo < static_cast<int64_t>(n_heads) * hd) return -7;
   VoWs w = carve_vo(ws, d, n_heads, n_kv_heads, hd);
   if (ws_bytes < w.bytes) return -10;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t dp = mg::round_up(d, 64);
   const int64_t nv = static_cast<int64_t>(n_kv_heads) * hd, vp = mg::round_up(nv, 64);
-  const int group = n_heads / n_kv_heads;
-  const bool mha = group == 1;
+  const bool mha = n_heads == n_kv_heads;
   const bf16* wv = static_cast<const bf16*>(Wv);
   const bf16* wo = static_cast<const bf16*>(Wo);
+  const int parts1 = gram_parts(n_kv_heads);
   int rc;
 
-  // planes of C + rho I (full symmetric matrix) and W_v^T
-  if ((rc = mg::split_planes(Cx, ldc, d, d, w.c_planes, dp, d * dp, false, nullptr, s, ridge)))
-    return rc;
+  cudaMemsetAsync(info, 0, sizeof(int), s);
   transpose_bf16_kernel<<<dim3(static_cast<unsigned>((d + 31) / 32),
                                static_cast<unsigned>((nv + 31) / 32)),
                           256, 0, s>>>(wv, ldwv, nv, d, w.wvt, vp);
   if ((rc = cuda_rc())) return rc;
-  // P = (C + rho I) W_v^T   [d, nv]
-  {
-    mg::GemmArgs g{};
-    g.A = w.c_planes;
-    g.lda = dp;
-    g.a_plane_stride = d * dp;
-    g.a_planes = kPlanes;
-    g.B = w.wvt;
-    g.ldb = vp;
-    g.b_planes = 1;
-    g.npairs = 3;
-    for (int i = 0; i < 3; ++i) {
-      g.pair_a[i] = i;
-      g.pair_b[i] = 0;
+
+  if (method == MG_VO_FACTOR) {
+    // ---- C + rho I = U^T U  (blocked Cholesky, fp32 storage, fp64 diagonal blocks)
+    copy_upper_ridge_kernel<<<dim3(static_cast<unsigned>((d + 1023) / 1024 < 8 ? (d + 1023) / 1024 : 8),
+                                   static_cast<unsigned>(d)),
+                              256, 0, s>>>(Cx, ldc, w.a, dp, d, ridge);
+    if ((rc = cuda_rc())) return rc;
+    {
+      mg::LaneScope scope(s, d);
+      if ((rc = mg::cholesky_upper(w.a, d, dp, w.chol, info, scope.lanes()))) return rc;
     }
-    g.M = d;
-    g.N = nv;
-    g.K = d;
-    g.D = w.p;
-    g.ldd = vp;
-    g.alpha = 1.f;
-    g.tiles = mg::TILES_FULL;
-    g.epi = mg::EPI_STORE;
-    g.ksplit = 1;
-    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
-  }
-  if ((rc = mg::split_planes(w.p, vp, d, nv, w.p_planes, vp, d * vp, false, nullptr, s))) return rc;
-  // G1[h] = W_v,h P_h  (diagonal hd x hd blocks of W_v P)
-  cudaMemsetAsync(w.g1, 0, sizeof(float) * n_kv_heads * hd * hd, s);
-  {
-    mg::GemmArgs g{};
-    g.A = w.wvt;
-    g.lda = vp;
-    g.a_planes = 1;
-    g.B = w.p_planes;
-    g.ldb = vp;
-    g.b_plane_stride = d * vp;
-    g.b_planes = kPlanes;
-    g.npairs = 3;
-    for (int i = 0; i < 3; ++i) {
-      g.pair_a[i] = 0;
-      g.pair_b[i] = i;
+    // planes of U^T (lower triangular, explicit zeros above the diagonal)
+    if ((rc = mg::split_planes(w.a, dp, d, d, w.ut_planes, dp, dp * dp, true, nullptr, s, 0.f, true)))
+      return rc;
+    // M^T[nv, d] = W_v U^T :  D[m, n] = sum_k wvt[k, m] * Ut[k, n],  Ut[k, n] = U[n, k] = 0 for n > k
+    {
+      mg::GemmArgs g{};
+      g.A = w.wvt;
+      g.lda = vp;
+      g.a_planes = 1;
+      g.B = w.ut_planes;
+      g.ldb = dp;
+      g.b_plane_stride = dp * dp;
+      g.b_planes = kPlanes;
+      g.npairs = 3;
+      for (int i = 0; i < 3; ++i) {
+        g.pair_a[i] = 0;
+        g.pair_b[i] = i;
+      }
+      g.M = nv;
+      g.N = d;
+      g.K = d;
+      g.D = w.mt;
+      g.ldd = dp;
+      g.alpha = 1.f;
+      g.tiles = mg::TILES_FULL;
+      g.epi = mg::EPI_STORE;
+      g.ksplit = 1;
+      g.klo_from_n = 1;
+      if ((rc = mg::gemm_tn_launch(g, s))) return rc;
     }
-    g.M = g.N = nv;
-    g.K = d;
-    g.D = w.g1;
-    g.ldd = hd;
-    g.alpha = 1.f;
-    g.tiles = mg::TILES_DIAG;
-    g.epi = mg::EPI_ADD;
-    g.hd = hd;
-    g.ksplit = 0;
-    if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    // G1[h] = M_h^T M_h in fp64: rows h*hd .. of M^T, reduction over its d columns
+    rc = launch_gram64<float, float>(w.mt, static_cast<int64_t>(hd) * dp, dp, 1, w.mt,
+                                     static_cast<int64_t>(hd) * dp, dp, 1, true, n_kv_heads, hd, d,
+                                     parts1, w.g1, s);
+    if (rc) return rc;
+  } else {
+    // ---- Gram route: P = (C + rho I) W_v^T on the tensor cores (fp32), G1[h] = W_v,h P_h in fp64.
+    //      Works for any symmetric C (no factorisation to break down) but the fp32 rounding of P
+    //      costs ~2^-24 (sigma_1 / sigma_r)^2 in the small singular values.
+    if ((rc = mg::split_planes(Cx, ldc, d, d, w.ut_planes, dp, dp * dp, false, nullptr, s, ridge)))
+      return rc;
+    {
+      mg::GemmArgs g{};
+      g.A = w.ut_planes;
+      g.lda = dp;
+      g.a_plane_stride = dp * dp;
+      g.a_planes = kPlanes;
+      g.B = w.wvt;
+      g.ldb = vp;
+      g.b_planes = 1;
+      g.npairs = 3;
+      for (int i = 0; i < 3; ++i) {
+        g.pair_a[i] = i;
+        g.pair_b[i] = 0;
+      }
+      g.M = d;
+      g.N = nv;
+      g.K = d;
+      g.D = w.mt;
+      g.ldd = vp;
+      g.alpha = 1.f;
+      g.tiles = mg::TILES_FULL;
+      g.epi = mg::EPI_STORE;     // one accumulation run per tile: deterministic
+      g.ksplit = 1;
+      if ((rc = mg::gemm_tn_launch(g, s))) return rc;
+    }
+    // X(a, c) = W_v[h*hd + a, c] (bf16),  Y(b, c) = P[c, h*hd + b] (fp32)
+    rc = launch_gram64<bf16, float>(wv, static_cast<int64_t>(hd) * ldwv, ldwv, 1, w.mt, hd, 1, vp, false,
+                                    n_kv_heads, hd, d, parts1, w.g1, s);
+    if (rc) return rc;
   }
   if (mha) {
-    cudaMemsetAsync(w.g2, 0, sizeof(float) * n_heads * hd * hd, s);
-    rc = mg_syrk_heads_bf16_f32(wo, d, static_cast<int64_t>(n_heads) * hd, ldwo, hd, w.g2, 1.f, 1,
-                                stream);
-    if (rc) return rc;
+    if (tensor_hd(hd)) {
+      // overwrite mode = one accumulation run per tile, no split-K: results do not depend on timing
+      rc = mg_syrk_heads_bf16_f32(wo, d, static_cast<int64_t>(n_heads) * hd, ldwo, hd, w.g2f, 1.f, 0,
+                                  stream);
+      if (rc) return rc;
+      const int64_t cnt = static_cast<int64_t>(n_heads) * hd * hd;
+      f32_to_f64_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, s>>>(w.g2f, w.g2, cnt);
+      if ((rc = cuda_rc())) return rc;
+    } else {
+      // X(a, c) = W_o[c, h*hd + a]
+      rc = launch_gram64<bf16, bf16>(wo, hd, 1, ldwo, wo, hd, 1, ldwo, true, n_heads, hd, d,
+                                     gram_parts(n_heads), w.g2, s);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
 
 int mg_vo_finish(const void* Wv, int64_t ldwv, const void* Wo, int64_t ldwo, int n_heads,
                  int n_kv_heads, int hd, int64_t d, int r, void* Wv_out, int64_t ldv_out,
-                 void* Wo_out, int64_t ldo_out, void* ws, size_t ws_bytes, void* stream) {
+                 void* Wo_out, int64_t ldo_out, int out_f32, void* ws, size_t ws_bytes,
+                 void* stream) {
   if (!Wv || !Wo || !Wv_out || !Wo_out || !ws) return -1;
   if (d <= 0 || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads) return -2;
-  if (hd != 32 && hd != 64 && hd != 128) return -6;
+  if (!valid_hd(hd)) return -6;
   if (r <= 0 || r > hd) return -11;
   if (ldwv < d || ldwo < static_cast<int64_t>(n_heads) * hd || ldv_out < d ||
       ldo_out < static_cast<int64_t>(n_heads) * r)
@@ -651,44 +883,59 @@ int mg_vo_finish(const void* Wv, int64_t ldwv, const void* Wo, int64_t ldwo, int
   const bf16* wv = static_cast<const bf16*>(Wv);
   const bf16* wo = static_cast<const bf16*>(Wo);
   int rc;
-  static bool attr_set = false;
   const size_t esm = eig_smem_bytes(hd);
   const size_t osm = sizeof(float) * (hd * r + 64 * (hd + 1));
-  if (!attr_set) {
+  static mg::PerDeviceOnce once;
+  rc = once.run([] {
+    const int o_max = static_cast<int>(sizeof(float) * (kMaxHd * kMaxHd + 64 * (kMaxHd + 1)));
+    const int v_max = static_cast<int>(sizeof(float) * kMaxHd * kMaxHd);
     cudaError_t e = cudaFuncSetAttribute(vo_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(eig_smem_bytes(kMaxHd)));
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(vo_apply_o_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(float) * (kMaxHd * kMaxHd + 64 * (kMaxHd + 1))));
+      e = cudaFuncSetAttribute(vo_apply_o_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, o_max);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(vo_apply_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(float) * kMaxHd * kMaxHd));
-    if (e != cudaSuccess) return -1000 - static_cast<int>(e);
-    attr_set = true;
+      e = cudaFuncSetAttribute(vo_apply_o_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, o_max);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(vo_apply_v_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, v_max);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(vo_apply_v_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, v_max);
+    return e;
+  });
+  if (rc) return rc;
+  const int parts2 = tensor_hd(hd) ? 1 : gram_parts(n_heads);
+  vo_factor_kernel<<<n_kv_heads, 1024, esm, s>>>(w.g1, gram_parts(n_kv_heads), mha ? w.g2 : nullptr,
+                                                 parts2, hd, r, w.scratch, w.rv, w.ro);
+  if ((rc = cuda_rc())) return rc;
+  const dim3 gv(static_cast<unsigned>((d + 63) / 64), n_kv_heads);
+  const dim3 go(static_cast<unsigned>((d + 63) / 64), n_heads);
+  const size_t vsm = sizeof(float) * hd * r;
+  if (out_f32) {
+    vo_apply_v_kernel<float><<<gv, 256, vsm, s>>>(wv, ldwv, w.rv, hd, r, d,
+                                                  static_cast<float*>(Wv_out), ldv_out);
+    if ((rc = cuda_rc())) return rc;
+    vo_apply_o_kernel<float><<<go, 256, osm, s>>>(wo, ldwo, w.ro, group, hd, r, d,
+                                                  static_cast<float*>(Wo_out), ldo_out);
+  } else {
+    vo_apply_v_kernel<bf16><<<gv, 256, vsm, s>>>(wv, ldwv, w.rv, hd, r, d,
+                                                 static_cast<bf16*>(Wv_out), ldv_out);
+    if ((rc = cuda_rc())) return rc;
+    vo_apply_o_kernel<bf16><<<go, 256, osm, s>>>(wo, ldwo, w.ro, group, hd, r, d,
+                                                 static_cast<bf16*>(Wo_out), ldo_out);
   }
-  vo_factor_kernel<<<n_kv_heads, 1024, esm, s>>>(w.g1, mha ? w.g2 : nullptr, hd, r, w.scratch, w.rv,
-                                                 w.ro);
-  if ((rc = cuda_rc())) return rc;
-  vo_apply_v_kernel<<<dim3(static_cast<unsigned>((d + 63) / 64), n_kv_heads), 256,
-                      sizeof(float) * hd * r, s>>>(wv, ldwv, w.rv, hd, r, d,
-                                                   static_cast<bf16*>(Wv_out), ldv_out);
-  if ((rc = cuda_rc())) return rc;
-  vo_apply_o_kernel<<<dim3(static_cast<unsigned>((d + 63) / 64), n_heads), 256, osm, s>>>(
-      wo, ldwo, w.ro, group, hd, r, d, static_cast<bf16*>(Wo_out), ldo_out);
   return cuda_rc();
 }
 
 int mg_vo_compress(const float* Cx, int64_t ldc, float ridge, const void* Wv, int64_t ldwv,
                    const void* Wo, int64_t ldwo, int n_heads, int n_kv_heads, int hd, int64_t d,
-                   int r, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out, void* ws,
-                   size_t ws_bytes, void* stream) {
+                   int r, int method, void* Wv_out, int64_t ldv_out, void* Wo_out, int64_t ldo_out,
+                   int out_f32, int* info, void* ws, size_t ws_bytes, void* stream) {
   if (!Wv_out || !Wo_out) return -1;
   if (r <= 0 || r > hd) return -11;
-  int rc = mg_vo_prepare(Cx, ldc, ridge, Wv, ldwv, Wo, ldwo, n_heads, n_kv_heads, hd, d, ws, ws_bytes,
-                         stream);
+  int rc = mg_vo_prepare(Cx, ldc, ridge, Wv, ldwv, Wo, ldwo, n_heads, n_kv_heads, hd, d, method, info,
+                         ws, ws_bytes, stream);
   if (rc) return rc;
   return mg_vo_finish(Wv, ldwv, Wo, ldwo, n_heads, n_kv_heads, hd, d, r, Wv_out, ldv_out, Wo_out,
-                      ldo_out, ws, ws_bytes, stream);
+                      ldo_out, out_f32, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -56,6 +56,67 @@ def reduce_to_owner(t: torch.Tensor, layer_idx: int) -> bool:
     return owns(layer_idx)
 
 
+class LayerReducer:
+    """Reduce-as-you-go exchange of one layer's statistics.
+
+    `submit(layer, c_mlp, c_x, c_q, c_k)` is called on the stream that produced the sums (in the
+    last local batch, as soon as the layer's hooks have fired).  On a side stream it packs the two
+    symmetric accumulators' upper triangles and the per-head blocks into ONE contiguous fp32
+    buffer (half the bytes of the square matrices, one collective instead of four), reduces it to
+    the layer's owner over NCCL and, on the owner, scatters the sum back — all of it overlapped
+    with the forward of the following layers.  `wait()` joins the side stream.  Every rank submits
+    the layers in the same order, so the collectives match up.
+
+    CPU tensors (the gloo tests of this plumbing) take four plain reductions: the pack kernels
+    are CUDA-only and the product path never holds statistics on the host."""
+
+    def __init__(self):
+        self._side = None
+        self._buf = None
+
+    def submit(self, layer_idx: int, c_mlp, c_x, c_q, c_k) -> bool:
+        mine = owns(layer_idx)
+        if not is_distributed():
+            return mine
+        if not c_mlp.is_cuda:
+            for t in (c_mlp, c_x, c_q, c_k):
+                dist.reduce(t, dst=owner_of(layer_idx), op=dist.ReduceOp.SUM)
+            return mine
+        from . import ops
+
+        dev = c_mlp.device
+        n1, n2 = c_mlp.shape[0], c_x.shape[0]
+        sizes = [ops.packed_upper_numel(n1), ops.packed_upper_numel(n2), c_q.numel(), c_k.numel()]
+        total = sum(sizes)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        if self._buf is None or self._buf.numel() < total:
+            self._buf = torch.empty(total, dtype=torch.float32, device=dev)
+            self._buf.record_stream(self._side)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        o1, o2, o3 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
+        buf = self._buf[:total]
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            ops.pack_upper_(buf[:o1], c_mlp)
+            ops.pack_upper_(buf[o1:o2], c_x)
+            buf[o2:o3].copy_(c_q.reshape(-1))
+            buf[o3:].copy_(c_k.reshape(-1))
+            dist.reduce(buf, dst=owner_of(layer_idx), op=dist.ReduceOp.SUM)
+            if mine:
+                ops.unpack_upper_(c_mlp, buf[:o1])
+                ops.unpack_upper_(c_x, buf[o1:o2])
+                c_q.copy_(buf[o2:o3].view_as(c_q))
+                c_k.copy_(buf[o3:].view_as(c_k))
+        return mine
+
+    def wait(self) -> None:
+        if self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+
+
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if is_distributed():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

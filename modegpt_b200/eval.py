@@ -57,9 +57,54 @@ def _hub_tokens(dataset: str, tokenizer, model, split: str, n: int, seed: int) -
     return chunks[pick]
 
 
+def _ce_chunk_rows() -> int:
+    return 8192          # rows of logits alive at once: 8192 x vocab bf16 (0.5 GB at vocab 32000)
+
+
+@torch.no_grad()
+def sequence_nll(model, x: torch.Tensor) -> torch.Tensor:
+    """Sum over the batch of next-token negative log-likelihoods (fp64 scalar on the device) for
+    token ids x [B, T], without materialising [B, T, vocab] logits: the decoder body runs once,
+    then row chunks of `hidden @ W_lm^T` (bf16) go through `mg_ce_rows_bf16`.  Equal to
+    CrossEntropyLoss(logits[:, :-1].float(), x[:, 1:]) * (T - 1) * B  (src/eval.py:205-212)."""
+    from . import ops
+
+    body = getattr(model, model.base_model_prefix, None)
+    head = model.get_output_embeddings()
+    fast = (body is not None and head is not None and x.is_cuda
+            and head.weight.dtype == torch.bfloat16)
+    if not fast:   # CPU / non-bf16 models (CPU tests): the plain formula
+        logits = model(x, use_cache=False).logits
+        loss = torch.nn.functional.cross_entropy(
+            logits[:, :-1, :].reshape(-1, logits.size(-1)).float(), x[:, 1:].reshape(-1), reduction="sum")
+        return loss.double()
+    hidden = body(x, use_cache=False).last_hidden_state            # [B, T, d], final norm applied
+    B, T, d = hidden.shape
+    h = hidden[:, :-1, :].reshape(-1, d)
+    labels = x[:, 1:].reshape(-1).contiguous()
+    total = torch.zeros((), dtype=torch.float64, device=x.device)
+    step = _ce_chunk_rows()
+    for r0 in range(0, h.shape[0], step):
+        logits = torch.nn.functional.linear(h[r0:r0 + step], head.weight, head.bias)
+        total += ops.ce_rows(logits, labels[r0:r0 + step]).double().sum()
+        del logits
+    return total
+
+
 @torch.no_grad()
 def compute_perplexity(model, tokenizer, bs: int = 16, device="cuda", dataset="wikitext",
-                       adapter=None, n_samples: int | None = None, seq_len: int | None = None) -> float:
+                       adapter=None, n_samples: int | None = None, seq_len: int | None = None,
+                       shard: bool = True) -> float:
+    """exp(sum of token NLLs / (N * (T - 1))) over fixed-length sequences (src/eval.py:134-225).
+    Differences underneath: chunked cross-entropy from bf16 logits (`sequence_nll`), the fused
+    elementwise / rebuilt-model kernels during the forward, and — with torch.distributed
+    initialised and shard=True — the sequences are dealt to ranks and the NLL sum is all-reduced
+    (every rank returns the same perplexity; all ranks must call)."""
+    import contextlib
+
+    from . import distributed as D
+    from .fused_forward import fused_elementwise, fused_rebuilt
+
     model.eval()
     dev = next(model.parameters()).device
     cfg = adapter.config if adapter is not None else None
@@ -71,17 +116,19 @@ def compute_perplexity(model, tokenizer, bs: int = 16, device="cuda", dataset="w
         tokens = _hub_tokens(dataset, tokenizer, model, split="test", n=n_samples or 512, seed=0)
         seq_len = tokens.shape[1]
     n = tokens.shape[0]
+    world, rank = (D.world_size(), D.rank()) if shard else (1, 0)
+    mine = tokens[rank::world]
     nll = torch.zeros((), dtype=torch.float64, device=dev)
     if dev.type == "cuda":
         torch.cuda.synchronize()
     t0 = time.perf_counter()
-    loss_fn = torch.nn.CrossEntropyLoss()
-    for i in range(0, n, bs):
-        x = tokens[i:i + bs].to(dev)
-        logits = model(x, use_cache=False).logits
-        loss = loss_fn(logits[:, :-1, :].reshape(-1, logits.size(-1)).float(), x[:, 1:].reshape(-1))
-        nll += loss.double() * (seq_len - 1) * x.shape[0]
-        del logits
+    fused = dev.type == "cuda" and not (cfg is not None and cfg.eager_forward)
+    with (fused_elementwise(model) if fused else contextlib.nullcontext()), \
+            (fused_rebuilt(model) if fused else contextlib.nullcontext()):
+        for i in range(0, mine.shape[0], bs):
+            nll += sequence_nll(model, mine[i:i + bs].to(dev))
+    if world > 1:
+        D.all_reduce_sum_(nll)
     if dev.type == "cuda":
         torch.cuda.synchronize()
     elapsed = time.perf_counter() - t0

@@ -87,3 +87,54 @@ def fused_elementwise(model):
     finally:
         for obj, name, old in reversed(saved):
             setattr(obj, name, old)
+
+
+@contextlib.contextmanager
+def fused_rebuilt(model):
+    """Kernel-backed `masked_rope` / `_masked_rms_norm` for a model rebuilt by the MoDeGPT flow
+    (patchers/*Rebuild.py, loaded through `auto_map`; those files stay self-contained torch code so
+    a checkpoint loads anywhere).  The reference gathers `cos[:, :, mask]` / `sin[:, :, mask]` on
+    every forward of every layer (src/patchers/LlamaRebuild.py:155-180) and runs the eager RoPE
+    sequence on the result; `mg_rope_masked_bf16` does the gather inside the rotation.  Same
+    arithmetic incl. the bf16 roundings (bit-exact RoPE; the masked RMS norm differs only in the
+    summation order)."""
+    module = sys.modules.get(type(model).__module__)
+    saved: list[tuple[object, str, object]] = []
+    try:
+        if module is not None and hasattr(module, "masked_rope"):
+            orig = module.masked_rope
+
+            def masked_rope(q, k, cos, sin, mask, groups, _orig=orig):
+                ok = (mask is not None and _is_fast(q) and _is_fast(k) and cos.dtype == q.dtype
+                      and q.dim() == 4 and cos.dim() == 3 and cos.is_contiguous() and sin.is_contiguous()
+                      and q.transpose(1, 2).is_contiguous() and k.transpose(1, 2).is_contiguous()
+                      and cos.shape[0] in (1, q.shape[0]) and q.shape[-1] % 2 == 0
+                      and mask.dtype == torch.int64 and mask.is_contiguous())
+                if not ok:
+                    return _orig(q, k, cos, sin, mask, groups)
+                qo = ops.rope_masked_bthr(q.transpose(1, 2), cos, sin, mask, groups).transpose(1, 2)
+                ko = ops.rope_masked_bthr(k.transpose(1, 2), cos, sin, mask, 1).transpose(1, 2)
+                return qo, ko
+
+            saved.append((module, "masked_rope", orig))
+            module.masked_rope = masked_rope
+            for name in dir(module):
+                cls = getattr(module, name)
+                if isinstance(cls, type) and "_masked_rms_norm" in cls.__dict__:
+                    orig_norm = cls.__dict__["_masked_rms_norm"]
+                    fn = orig_norm.__func__ if isinstance(orig_norm, staticmethod) else orig_norm
+
+                    def masked_norm(x, norm, mask, _fn=fn):
+                        # the Rebuild code hands the mask already repeated per query head
+                        if (_is_fast(x) and x.is_contiguous() and norm.weight.dtype == torch.bfloat16
+                                and x.shape[-1] <= 128 and mask.is_contiguous()
+                                and mask.shape[0] == x.shape[-2]):
+                            return ops.rmsnorm_masked(x, norm.weight, mask, 1, float(norm.variance_epsilon))
+                        return _fn(x, norm, mask)
+
+                    saved.append((cls, "_masked_rms_norm", orig_norm))
+                    setattr(cls, "_masked_rms_norm", staticmethod(masked_norm))
+        yield
+    finally:
+        for obj, name, old in reversed(saved):
+            setattr(obj, name, old)

@@ -93,8 +93,16 @@ def reload_compressed_model(model_dir: str, device="cuda:0", tokenizer_source: s
                 tokenizer.pad_token = tokenizer.eos_token
         except Exception as e:  # offline / tokenizer-less synthetic checkpoints
             logger.warning(f"no tokenizer loaded from {src!r}: {e}")
-    model = AutoModelForCausalLM.from_pretrained(model_dir, trust_remote_code=True, dtype="auto")
+    # The kernels take bf16 activations and weights (north_star: "bf16 activations, fp32
+    # accumulate") and the flow saves bf16 (the reference's convert_model creates bf16 Linears,
+    # model_adapter.py:199-208), so fp16 / fp32 checkpoints (facebook/opt-*, Llama-2-*-hf) are cast
+    # once at load instead of failing at the first calibration hook.
+    model = AutoModelForCausalLM.from_pretrained(model_dir, trust_remote_code=True, dtype=torch.bfloat16)
     model.to(device)
+    bad = {p.dtype for p in model.parameters() if p.is_floating_point() and p.dtype != torch.bfloat16}
+    if bad:
+        logger.info(f"casting {sorted(map(str, bad))} parameters to bfloat16")
+        model.to(torch.bfloat16)
     model.eval()
     return model, tokenizer
 

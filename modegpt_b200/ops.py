@@ -86,6 +86,30 @@ def scale_(x: torch.Tensor, scale: float) -> None:
     check("mg_scale_f32", lib.mg_scale_f32(x.data_ptr(), x.numel(), scale, _stream()))
 
 
+def packed_upper_numel(n: int) -> int:
+    return n * (n + 1) // 2
+
+
+def pack_upper_(packed: torch.Tensor, C: torch.Tensor) -> None:
+    """packed[n(n+1)/2] <- the upper triangle of C (row-major rows i..n-1): reduction wire format."""
+    n, m, ldc = _rowmajor_2d(C, "C")
+    if n != m or C.dtype != torch.float32 or packed.dtype != torch.float32:
+        raise ValueError("pack_upper_: C must be a square float32 matrix, packed float32")
+    if packed.numel() < packed_upper_numel(n) or not packed.is_contiguous():
+        raise ValueError("pack_upper_: packed buffer too small or not contiguous")
+    check("mg_pack_upper_f32", lib.mg_pack_upper_f32(C.data_ptr(), n, ldc, packed.data_ptr(), _stream()))
+
+
+def unpack_upper_(C: torch.Tensor, packed: torch.Tensor) -> None:
+    """Upper triangle of C <- packed (inverse of `pack_upper_`; the lower triangle is untouched)."""
+    n, m, ldc = _rowmajor_2d(C, "C")
+    if n != m or C.dtype != torch.float32 or packed.dtype != torch.float32:
+        raise ValueError("unpack_upper_: C must be a square float32 matrix, packed float32")
+    if packed.numel() < packed_upper_numel(n) or not packed.is_contiguous():
+        raise ValueError("unpack_upper_: packed buffer too small or not contiguous")
+    check("mg_unpack_upper_f32", lib.mg_unpack_upper_f32(packed.data_ptr(), n, C.data_ptr(), ldc, _stream()))
+
+
 # ------------------------------------------------------------------------------------------------
 # decompositions
 # ------------------------------------------------------------------------------------------------
@@ -199,43 +223,72 @@ def gather_head_rows(W: torch.Tensor, mask: torch.Tensor, n_heads: int, group: i
     return out
 
 
-def vo_compress(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int,
-                n_kv_heads: int, hd: int, r: int) -> tuple[torch.Tensor, torch.Tensor]:
-    """Type-III factors: (v_proj [KV*r, d], o_proj [d, H*r]) in bf16.  Cx full symmetric."""
+VO_FACTOR, VO_GRAM = 0, 1     # MG_VO_FACTOR / MG_VO_GRAM (include/modegpt_b200.h)
+
+
+def _vo_check(Cx, Wv, Wo, n_heads, n_kv_heads, hd, who):
     d, ldc = _f32_square(Cx, "Cx")
     _, _, ldwv = _rowmajor_2d(Wv, "Wv")
     _, _, ldwo = _rowmajor_2d(Wo, "Wo")
     if Wv.dtype != torch.bfloat16 or Wo.dtype != torch.bfloat16:
-        raise TypeError("vo_compress: weights must be bfloat16")
+        raise TypeError(f"{who}: weights must be bfloat16")
     if Wv.shape != (n_kv_heads * hd, d) or Wo.shape != (d, n_heads * hd):
-        raise ValueError("vo_compress: weight shapes do not match the head layout")
-    v_out = torch.empty(n_kv_heads * r, d, dtype=torch.bfloat16, device=Cx.device)
-    o_out = torch.empty(d, n_heads * r, dtype=torch.bfloat16, device=Cx.device)
+        raise ValueError(f"{who}: weight shapes do not match the head layout")
+    return d, ldc, ldwv, ldwo
+
+
+def vo_compress(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int,
+                n_kv_heads: int, hd: int, r: int, method: int = VO_GRAM,
+                out_dtype: torch.dtype = torch.bfloat16) -> tuple[torch.Tensor, torch.Tensor]:
+    """Type-III factors: (v_proj [KV*r, d], o_proj [d, H*r]) in bf16 (or the unrounded fp32 factors
+    with out_dtype=torch.float32).  Cx full symmetric.  method VO_GRAM (default): tensor-core
+    P = (Cx + ridge I) W_v^T, per-head Grams accumulated in fp64; VO_FACTOR: through the Cholesky
+    factor of Cx + ridge I (raises NotPositiveDefinite if that is singular in fp32)."""
+    d, ldc, ldwv, ldwo = _vo_check(Cx, Wv, Wo, n_heads, n_kv_heads, hd, "vo_compress")
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("vo_compress: out_dtype must be bfloat16 or float32")
+    v_out = torch.empty(n_kv_heads * r, d, dtype=out_dtype, device=Cx.device)
+    o_out = torch.empty(d, n_heads * r, dtype=out_dtype, device=Cx.device)
     nbytes = lib.mg_vo_ws_bytes(d, n_heads, n_kv_heads, hd)
     ws = _workspace(nbytes, Cx.device)
+    info = torch.zeros(1, dtype=torch.int32, device=Cx.device)
     check("mg_vo_compress",
           lib.mg_vo_compress(Cx.data_ptr(), ldc, ridge, Wv.data_ptr(), ldwv, Wo.data_ptr(), ldwo,
-                             n_heads, n_kv_heads, hd, d, r, v_out.data_ptr(), v_out.stride(0),
-                             o_out.data_ptr(), o_out.stride(0), ws.data_ptr(), nbytes, _stream()))
+                             n_heads, n_kv_heads, hd, d, r, method, v_out.data_ptr(), v_out.stride(0),
+                             o_out.data_ptr(), o_out.stride(0), int(out_dtype == torch.float32),
+                             info.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+    if method == VO_FACTOR:        # the Gram route has no pivots: no read-back, no sync
+        piv = int(info.item())
+        if piv:
+            raise NotPositiveDefinite("vo_compress", piv)
     return v_out, o_out
 
 
 def vo_prepare(Cx: torch.Tensor, ridge: float, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int,
-               n_kv_heads: int, hd: int) -> torch.Tensor:
-    """First half of `vo_compress` (the tensor-core part); returns the workspace for `vo_finish`."""
-    d, ldc = _f32_square(Cx, "Cx")
-    _, _, ldwv = _rowmajor_2d(Wv, "Wv")
-    _, _, ldwo = _rowmajor_2d(Wo, "Wo")
-    if Wv.dtype != torch.bfloat16 or Wo.dtype != torch.bfloat16:
-        raise TypeError("vo_prepare: weights must be bfloat16")
-    if Wv.shape != (n_kv_heads * hd, d) or Wo.shape != (d, n_heads * hd):
-        raise ValueError("vo_prepare: weight shapes do not match the head layout")
+               n_kv_heads: int, hd: int, method: int = VO_GRAM
+               ) -> tuple[torch.Tensor, torch.Tensor]:
+    """First half of `vo_compress` (tensor-core products + fp64 Grams); returns (workspace, info)
+    for `vo_finish`.  With method=VO_FACTOR, info[0] != 0 reports a non-positive Cholesky pivot
+    (Cx + ridge I singular in fp32); the Gram route never sets it."""
+    d, ldc, ldwv, ldwo = _vo_check(Cx, Wv, Wo, n_heads, n_kv_heads, hd, "vo_prepare")
     nbytes = lib.mg_vo_ws_bytes(d, n_heads, n_kv_heads, hd)
     ws = _workspace(nbytes, Cx.device)
+    info = torch.zeros(1, dtype=torch.int32, device=Cx.device)
     check("mg_vo_prepare",
           lib.mg_vo_prepare(Cx.data_ptr(), ldc, ridge, Wv.data_ptr(), ldwv, Wo.data_ptr(), ldwo,
-                            n_heads, n_kv_heads, hd, d, ws.data_ptr(), nbytes, _stream()))
-    return ws
+                            n_heads, n_kv_heads, hd, d, method, info.data_ptr(), ws.data_ptr(), nbytes,
+                            _stream()))
+    return ws, info
+
+
+def vo_prepare_into(ws: torch.Tensor, info: torch.Tensor, Cx, ridge, Wv, Wo, n_heads, n_kv_heads, hd,
+                    method: int) -> None:
+    """`vo_prepare` into an existing workspace (the retry with the other method)."""
+    d, ldc, ldwv, ldwo = _vo_check(Cx, Wv, Wo, n_heads, n_kv_heads, hd, "vo_prepare")
+    check("mg_vo_prepare",
+          lib.mg_vo_prepare(Cx.data_ptr(), ldc, ridge, Wv.data_ptr(), ldwv, Wo.data_ptr(), ldwo,
+                            n_heads, n_kv_heads, hd, d, method, info.data_ptr(), ws.data_ptr(),
+                            ws.numel(), _stream()))
 
 
 def vo_outputs(Wv: torch.Tensor, n_heads: int, n_kv_heads: int, r: int) -> tuple[torch.Tensor, torch.Tensor]:
@@ -256,7 +309,8 @@ def vo_finish(ws: torch.Tensor, Wv: torch.Tensor, Wo: torch.Tensor, n_heads: int
     check("mg_vo_finish",
           lib.mg_vo_finish(Wv.data_ptr(), Wv.stride(0), Wo.data_ptr(), Wo.stride(0), n_heads, n_kv_heads,
                            hd, d, r, v_out.data_ptr(), v_out.stride(0), o_out.data_ptr(),
-                           o_out.stride(0), ws.data_ptr(), ws.numel(), _stream()))
+                           o_out.stride(0), int(v_out.dtype == torch.float32), ws.data_ptr(),
+                           ws.numel(), _stream()))
     return v_out, o_out
 
 
@@ -293,3 +347,44 @@ def rope_bthd(x_bthd: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> tor
           lib.mg_rope_bf16(x_bthd.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, T, H,
                            hd, stride, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# rebuilt-model ops (masked RoPE / masked q-k norm) and the perplexity kernel
+# ------------------------------------------------------------------------------------------------
+def rope_masked_bthr(x_bthr: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, mask: torch.Tensor,
+                     group: int) -> torch.Tensor:
+    """Masked rotary embedding on a contiguous [B, T, H, r] bf16 tensor; cos / sin [1 or B, T, hd]
+    of the original head dim; mask [H / group, r] int64 (contiguous)."""
+    B, T, H, r = x_bthr.shape
+    out = torch.empty_like(x_bthr)
+    stride = 0 if cos.shape[0] == 1 else cos.stride(0)
+    check("mg_rope_masked_bf16",
+          lib.mg_rope_masked_bf16(x_bthr.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                                  mask.data_ptr(), B, T, H, group, r, cos.shape[-1], stride, _stream()))
+    return out
+
+
+def rmsnorm_masked(x: torch.Tensor, weight: torch.Tensor, mask: torch.Tensor, group: int,
+                   eps: float) -> torch.Tensor:
+    """x contiguous [..., H, r] bf16; weight [hd] bf16; mask [H / group, r] int64."""
+    H, r = x.shape[-2], x.shape[-1]
+    rows = x.numel() // (H * r)
+    out = torch.empty_like(x)
+    check("mg_rmsnorm_masked_bf16",
+          lib.mg_rmsnorm_masked_bf16(x.data_ptr(), rows, H, group, r, weight.data_ptr(), mask.data_ptr(),
+                                     eps, out.data_ptr(), _stream()))
+    return out
+
+
+def ce_rows(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """Per-row negative log-likelihood (fp32 [rows]) of bf16 logits [rows, vocab]."""
+    rows, vocab, ld = _rowmajor_2d(logits, "logits")
+    if logits.dtype != torch.bfloat16 or labels.dtype != torch.int64 or not labels.is_contiguous():
+        raise TypeError("ce_rows: logits bfloat16 [rows, vocab], labels contiguous int64 [rows]")
+    if labels.numel() != rows:
+        raise ValueError("ce_rows: one label per row")
+    nll = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    check("mg_ce_rows_bf16",
+          lib.mg_ce_rows_bf16(logits.data_ptr(), ld, rows, vocab, labels.data_ptr(), nll.data_ptr(), _stream()))
+    return nll

@@ -63,42 +63,6 @@ def _run_stages_serial(stages: dict, timings: dict, device: str) -> dict:
     return out
 
 
-def _run_stages_concurrent(stages: dict, timings: dict, device: str) -> dict:
-    """`--concurrent_stages`: the three decomposition types read disjoint statistics and weights and
-    write disjoint files, so they can run side by side, one host thread and one CUDA stream each.
-    Measured on Llama-2-7B: 31.7 vs 37.3 ms/layer with the in-memory hand-off, but slower than the
-    serial order once the layer files are written (the per-head Jacobi CTAs and the persistent
-    GEMM grids evict each other and the panel chain loses its free SMs) — hence opt-in."""
-    import threading
-
-    torch.cuda.synchronize()
-    out, errors = {}, []
-
-    def work(key, fn):
-        try:
-            torch.cuda.set_device(device)
-            stream = torch.cuda.Stream(device=device)
-            t0 = time.perf_counter()
-            with torch.no_grad(), torch.cuda.stream(stream):
-                out[key] = fn()
-            stream.synchronize()
-            timings[key] += time.perf_counter() - t0
-        except BaseException as e:       # re-raised on the main thread
-            errors.append(e)
-
-    t_all = time.perf_counter()
-    threads = [threading.Thread(target=work, args=kv, name=f"mg-stage-{kv[0]}") for kv in stages.items()]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    torch.cuda.synchronize()
-    timings["compress_wall_s"] += time.perf_counter() - t_all
-    if errors:
-        raise errors[0]
-    return out
-
-
 @torch.no_grad()
 def main(trial=None, config: CompressionConfig | None = None):
     _setup_logging()
@@ -114,12 +78,14 @@ def main(trial=None, config: CompressionConfig | None = None):
     model, tokenizer = reload_compressed_model(config.model, device=device)
     adapter = ModelAdapter.from_model(model=model, tokenizer=tokenizer)
     adapter.config = config
+    adapter.validate_for_kernels()     # fail here, not after calibration
     adapter.metrics["note"] = config.note
 
+    # held-out sequences are dealt to the ranks, the NLL sum is all-reduced (eval.compute_perplexity)
+    baseline = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
     if is_root:
-        baseline = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
         logger.info(f"Baseline ppl: {baseline}")
-        adapter.metrics["baseline-ppl"] = baseline
+    adapter.metrics["baseline-ppl"] = baseline
 
     adapter.prepare_writer()      # writer threads + 384 MB of pinned bounce buffers, before the timed stages
     n_layers = adapter.n_layers
@@ -182,8 +148,7 @@ def main(trial=None, config: CompressionConfig | None = None):
         if "vo" in config.order:
             stages["vo_s"] = lambda: compress_vo(adapter=adapter, cov=cov_x, keep_ratios=keep,
                                                  target_layers=target)
-        results = (_run_stages_concurrent if config.concurrent_stages else _run_stages_serial)(
-            stages, timings, device)
+        results = _run_stages_serial(stages, timings, device)
         rotary_masks.extend(results.get("qk_s") or [])
         del cov_mlp, cov_q, cov_k, cov_x, stages
         gc.collect()
@@ -202,21 +167,23 @@ def main(trial=None, config: CompressionConfig | None = None):
     adapter.metrics.update({**timings, "calib_tokens_per_s": tokens / max(timings["calibration_s"], 1e-9),
                             "compress_s_per_layer": (compress_wall + timings["file_flush_s"]) / n_layers,
                             "world_size": D.world_size()})
-    if not is_root:
-        return None
-
-    suffixes = [s for s in ("mlp", "qk", "vo") if s in config.order]
-    adapter.convert_model(saved_layers_dir=config.temp_storage_dir, suffixes=suffixes)
-    adapter.patch_config()
-    save_compressed_model(adapter, rotary_masks=rotary_masks if "qk" in config.order else None,
-                          save_dir=save_dir, source_model_name=config.model)
+    if is_root:
+        suffixes = [s for s in ("mlp", "qk", "vo") if s in config.order]
+        adapter.convert_model(saved_layers_dir=config.temp_storage_dir, suffixes=suffixes)
+        adapter.patch_config()
+        save_compressed_model(adapter, rotary_masks=rotary_masks if "qk" in config.order else None,
+                              save_dir=save_dir, source_model_name=config.model)
     del model
+    adapter.model = None
     gc.collect()
     torch.cuda.empty_cache()
-
+    D.barrier()   # the checkpoint is on disk: every rank reloads it and takes its share of the
+                  # held-out sequences (token-sharded perplexity)
     model, tokenizer = reload_compressed_model(save_dir, device=device)
     adapter.model, adapter.tokenizer = model, tokenizer
     ppl = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
+    if not is_root:
+        return None
     adapter.metrics[f"ppl-{config.dataset}"] = ppl
     adapter.save_metrics()
     logger.info(f"Compressed (PPL): {ppl}")

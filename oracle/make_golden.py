@@ -181,6 +181,107 @@ def golden_vo(ref, rng):
     np.savez_compressed(OUT / "vo.npz", **out)
 
 
+def golden_vo_illcond(ref):
+    """Ill-conditioned type-III fixture: per-channel scale spread 1.5 (cond(C) >= 1e6 by far), so the
+    small singular values of sqrt(C) W_v^T sit many orders below the first one.  C is stored in
+    float32 and handed to the reference as exactly those values, so the reference and the CUDA path
+    see the same input.  Own generator: the older fixtures keep their random streams."""
+    rng = np.random.default_rng(771)
+    d, hd, rank, heads = 256, 64, 48, 4
+    x = rng.standard_normal((2048, d)) * np.exp(1.5 * rng.standard_normal(d))
+    c32 = (x.T @ x / x.shape[0]).astype(np.float32)
+    c = torch.tensor(c32.astype(np.float64))
+    root = ref.cu.sqrt_M(c, ridge_lambda=1e-5)
+    root_inv = torch.linalg.inv(root)
+    wv = torch.tensor(rng.standard_normal((heads * hd, d)) * 0.05).to(torch.bfloat16)
+    wo = torch.tensor(rng.standard_normal((d, heads * hd)) * 0.05).to(torch.bfloat16)
+    out = dict(c=c32, ridge=np.array(1e-5), rank=np.array(rank), hd=np.array(hd), heads=np.array(heads),
+               wv=bf16_bits(wv), wo=bf16_bits(wo))
+    ev = np.linalg.eigvalsh(c32.astype(np.float64))
+    g1 = f64(wv[:hd]) @ (c32.astype(np.float64) + 1e-5 * np.eye(d)) @ f64(wv[:hd]).T
+    eg = np.linalg.eigvalsh(g1)
+    out.update(cond_c=np.array(ev[-1] / max(ev[0], 1e-300)), cond_g1=np.array(eg[-1] / eg[0]),
+               sigma_ratio=np.array(np.sqrt(eg[-1] / eg[-rank])))
+    vs, os_ = [], []
+    for h in range(heads):
+        ref.vo.compress_head(h, hd, rank, wv, wo, root, root_inv, vs, os_)
+    out.update(mha_v=np.concatenate([f64(t) for t in vs], 0), mha_o=np.concatenate([f64(t) for t in os_], 1))
+    # GQA: 2 kv heads x 2 query heads each (the first 2*hd rows of W_v)
+    vs, os_ = [], []
+    for h in range(2):
+        ref.vo.compress_head_grouped(h, 2, hd, rank, wv[:2 * hd], wo, root, root_inv, vs, os_)
+    out.update(gqa_v=np.concatenate([f64(t) for t in vs], 0), gqa_o=np.concatenate([f64(t) for t in os_], 1))
+    np.savez_compressed(OUT / "vo_illcond.npz", **out)
+
+
+def golden_pipeline_opt(ref):
+    """BASELINE config #1 in miniature: the oracle-level OPT pipeline (oracle/opt_pipeline.py) on a
+    tiny random-init OPT.  The reference's OPT adapter cannot be instantiated, so the
+    pipeline is composed from the pinned oracle functions — and cross-checked here, head by head,
+    against the reference's own surviving functions: `compress_head_opt` (compress_qk.py:439-476),
+    `compress_head` (compress_vo.py:162-223) and `get_ridge_scores` (compress_mlp.py:13-25)."""
+    from transformers import AutoModelForCausalLM, OPTConfig
+
+    from oracle import modegpt_oracle as O
+    from oracle import opt_pipeline
+
+    torch.manual_seed(0)
+    d, H, hd, ffn, L = 128, 4, 32, 256, 3
+    cfg = OPTConfig(hidden_size=d, num_attention_heads=H, ffn_dim=ffn, num_hidden_layers=L, vocab_size=160,
+                    max_position_embeddings=256, word_embed_proj_dim=d, do_layer_norm_before=True)
+    model = AutoModelForCausalLM.from_config(cfg).to(torch.bfloat16).eval()
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for blk in model.model.decoder.layers:      # HF initialises biases to zero: make them count
+            for lin in (blk.fc1, blk.fc2, blk.self_attn.q_proj, blk.self_attn.k_proj,
+                        blk.self_attn.v_proj, blk.self_attn.out_proj):
+                lin.bias.copy_((0.05 * torch.randn(lin.bias.shape, generator=g)).to(torch.bfloat16))
+            blk.fc1.weight.mul_(torch.exp(0.6 * torch.randn(ffn, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn.q_proj.weight.mul_(torch.exp(0.6 * torch.randn(d, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn.k_proj.weight.mul_(torch.exp(0.6 * torch.randn(d, 1, generator=g)).to(torch.bfloat16))
+            blk.self_attn_layer_norm.weight.mul_(torch.exp(0.5 * torch.randn(d, generator=g)).to(torch.bfloat16))
+    tokens = torch.randint(0, 160, (4, 96), generator=torch.Generator().manual_seed(1234))
+    hyper = dict(compression_ratio=0.3, nystrom_ridge=1e-4, ridge_vo=1e-5, smoothing=0.04948, max_sparsity=0.95)
+    res = opt_pipeline.run(model, [tokens[0:2], tokens[2:4]], **hyper)
+
+    # ---- cross-check against the reference's surviving OPT functions
+    sd = model.state_dict()
+    for l in range(L):
+        pre = f"model.decoder.layers.{l}."
+        r_mlp, r_qk, r_vo = (int(x) for x in res[f"L{l}_ranks"])
+        scores = ref.mlp.get_ridge_scores(torch.tensor(res[f"cov_mlp{l}"]), l, 1e-4)
+        assert np.allclose(f64(scores), O.ridge_scores(res[f"cov_mlp{l}"], 1e-4), rtol=1e-9)
+        wq, wk = sd[pre + "self_attn.q_proj.weight"], sd[pre + "self_attn.k_proj.weight"]
+        bq, bk = sd[pre + "self_attn.q_proj.bias"], sd[pre + "self_attn.k_proj.bias"]
+        root = ref.cu.sqrt_M(torch.tensor(res[f"cov_x{l}"]), ridge_lambda=1e-5)
+        root_inv = torch.linalg.inv(root)
+        vs, os_ = [], []
+        for h in range(H):
+            qo, ko, bqo, bko = [], [], [], []
+            sl = slice(h * hd, (h + 1) * hd)
+            ref.qk.compress_head_opt(torch.tensor(res[f"cov_q{l}"][h]), torch.tensor(res[f"cov_k{l}"][h]),
+                                     wq[sl], wk[sl], bq[sl], bk[sl], qo, ko, bqo, bko, rank=r_qk)
+            assert np.array_equal(f64(qo[0]), res[f"L{l}_qk_q_proj"][h * r_qk:(h + 1) * r_qk].astype(np.float64))
+            assert np.array_equal(f64(ko[0]), res[f"L{l}_qk_k_proj"][h * r_qk:(h + 1) * r_qk].astype(np.float64))
+            assert np.array_equal(f64(bqo[0]), res[f"L{l}_qk_q_bias"][h * r_qk:(h + 1) * r_qk].astype(np.float64))
+            ref.vo.compress_head(h, hd, r_vo, sd[pre + "self_attn.v_proj.weight"],
+                                 sd[pre + "self_attn.out_proj.weight"], root, root_inv, vs, os_)
+        v_ref = np.concatenate([f64(t) for t in vs], 0)
+        o_ref = np.concatenate([f64(t) for t in os_], 1)
+        sgn = np.sign(np.sum(res[f"L{l}_vo_v64"] * v_ref, axis=1))
+        assert np.linalg.norm(res[f"L{l}_vo_v64"] * sgn[:, None] - v_ref) / np.linalg.norm(v_ref) < 1e-7
+        assert np.linalg.norm(res[f"L{l}_vo_o64"] * sgn[None, :] - o_ref) / np.linalg.norm(o_ref) < 1e-7
+
+    out = {"tokens": tokens.numpy(), "cfg": np.array([d, ffn, L, H, H, hd, 160]),
+           "hyper": np.array([hyper["compression_ratio"], hyper["nystrom_ridge"], hyper["ridge_vo"],
+                              hyper["smoothing"], hyper["max_sparsity"]])}
+    for k, v in model.state_dict().items():
+        out["w:" + k] = bf16_bits(v)
+    for k, v in res.items():
+        out[k] = np.asarray(v)
+    np.savez_compressed(OUT / "pipeline_opt.npz", **out)
+
+
 def golden_pipeline(ref, tag: str, n_kv: int, qwen: bool = False):
     """Whole reference pipeline (calibration -> allocation -> type I/II/III) on a tiny random-init
     model, recording the hook inputs so kernels can be checked on identical activations."""
@@ -261,11 +362,21 @@ def golden_pipeline(ref, tag: str, n_kv: int, qwen: bool = False):
     np.savez_compressed(OUT / f"pipeline_{tag}.npz", **out)
 
 
-def main():
+def main(only: str | None = None):
     if not REF.exists():
         raise SystemExit(f"{REF} not found: goldens can only be generated where the reference is mounted")
     install_cpu_shim()
     sys.path.insert(0, str(REF))
+    # make `oracle` importable WITHOUT putting the repo root on sys.path: the repo's own `src/`
+    # alias package (a regular package) would shadow the reference's `src/` (a namespace package)
+    import importlib.util
+
+    here = Path(__file__).resolve().parent
+    spec = importlib.util.spec_from_file_location("oracle", here / "__init__.py",
+                                                  submodule_search_locations=[str(here)])
+    pkg = importlib.util.module_from_spec(spec)
+    sys.modules["oracle"] = pkg
+    spec.loader.exec_module(pkg)
     os.chdir(tempfile.mkdtemp(prefix="mg_golden_cwd_"))   # the reference writes ./metrics, ./logs
     import src.adapters.CompressionConfig as cc
     import src.adapters.model_adapter as ma
@@ -278,17 +389,24 @@ def main():
     ref = types.SimpleNamespace(cc=cc, ma=ma, cal=cal, mlp=mlp, qk=qk, vo=vo, cu=cu)
     OUT.mkdir(parents=True, exist_ok=True)
     rng = np.random.default_rng(20240917)
+    # fixtures with their own generators can be (re)made alone: `make_golden.py --only NAME`
+    standalone = {"vo_illcond": golden_vo_illcond, "pipeline_opt": golden_pipeline_opt}
     with torch.no_grad():
-        golden_utils(ref, rng)
-        golden_mlp(ref, rng)
-        golden_qk(ref, rng)
-        golden_vo(ref, rng)
-        golden_pipeline(ref, "llama_mha", n_kv=4)
-        golden_pipeline(ref, "llama_gqa", n_kv=2)
-        golden_pipeline(ref, "qwen3_gqa", n_kv=2, qwen=True)
+        if only is not None:
+            standalone[only](ref)
+        else:
+            golden_utils(ref, rng)     # these four share one random stream: keep the order
+            golden_mlp(ref, rng)
+            golden_qk(ref, rng)
+            golden_vo(ref, rng)
+            for fn in standalone.values():
+                fn(ref)
+            golden_pipeline(ref, "llama_mha", n_kv=4)
+            golden_pipeline(ref, "llama_gqa", n_kv=2)
+            golden_pipeline(ref, "qwen3_gqa", n_kv=2, qwen=True)
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None)

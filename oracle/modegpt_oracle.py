@@ -128,6 +128,16 @@ def sqrt_psd(m: np.ndarray, ridge: float = 1e-4, inverse: bool = False):
 # --------------------------------------------------------------------------------------------
 
 
+def _solve_lower(low: np.ndarray, rhs: np.ndarray, trans: bool = False) -> np.ndarray:
+    """low^-1 rhs (or low^-T rhs) by a triangular solve — the flop count of the reference's
+    cholesky_inverse / cholesky_solve, so the CPU baseline is not charged an LU it never does."""
+    try:
+        from scipy.linalg import solve_triangular
+    except ImportError:                                # numpy only: LU of a triangular matrix
+        return np.linalg.solve(low.T if trans else low, rhs)
+    return solve_triangular(low, rhs, lower=True, trans="T" if trans else "N", check_finite=False)
+
+
 def ridge_scores(c: np.ndarray, ridge: float) -> np.ndarray:
     """diag((C + ridge*I)^-1) through a Cholesky factorisation (compress_mlp.py:13-25)."""
     c = np.asarray(c, dtype=np.float64)
@@ -136,7 +146,7 @@ def ridge_scores(c: np.ndarray, ridge: float) -> np.ndarray:
     # that reaches the fp64 sum is float32(ridge).
     ridge = float(np.float32(ridge))
     low = np.linalg.cholesky(c + ridge * np.eye(n))
-    low_inv = np.linalg.solve(low, np.eye(n))  # any exact route to the inverse diagonal
+    low_inv = _solve_lower(low, np.eye(n))     # any exact route to the inverse diagonal
     return np.sum(low_inv * low_inv, axis=0)
 
 
@@ -161,8 +171,8 @@ def nystrom_mlp(w_up, w_gate, w_down, c, keep_ratio: float, ridge: float):
     c_kk = c[np.ix_(idx, idx)]
     cross = c[idx, :] @ w_down.T                      # [r, d]
     low = np.linalg.cholesky(c_kk + 1e-6 * np.eye(rank))
-    y = np.linalg.solve(low, cross)
-    down_t = np.linalg.solve(low.T, y)                # [r, d] == cholesky_solve(cross, L)
+    y = _solve_lower(low, cross)
+    down_t = _solve_lower(low, y, trans=True)         # [r, d] == cholesky_solve(cross, L)
     out = {"up": to_bf16(up), "down": to_bf16(down_t.T)}
     if gate is not None:
         out["gate"] = to_bf16(gate)

@@ -125,6 +125,17 @@ def _gloo_worker(rank, world, port, out_dir):
         assert owner == (layer % world == rank)
         if owner:
             assert torch.all(t == sum(range(1, world + 1)))
+    # one layer's four statistics through the reducer (CPU tensors: plain reductions; on CUDA the
+    # same call packs the upper triangles into one buffer — tests/test_gpu_kernels.py, dist_check)
+    red = D.LayerReducer()
+    for layer in range(n_layers):
+        ts = [torch.full(shape, float(rank + 1 + layer)) for shape in ((6, 6), (4, 4), (2, 3, 3), (1, 3, 3))]
+        mine = red.submit(layer, *ts)
+        red.wait()
+        assert mine == (layer % world == rank)
+        if mine:
+            for t in ts:
+                assert torch.all(t == sum(r + 1 + layer for r in range(world)))
     assert D.owned_layers(range(n_layers)) == [l for l in range(n_layers) if l % world == rank]
     full = D.gather_by_layer({l: torch.tensor([l, rank]) for l in D.owned_layers(range(n_layers))}, n_layers)
     assert [int(x[0]) for x in full] == list(range(n_layers))

@@ -249,56 +249,23 @@ def test_type2_matches_oracle(ops, H, KV, hd, r, mode, arch):
         ops.gather_head_rows(wk.to(DEV), mask, KV, 1, hd).float().cpu().numpy(), want["k_proj"])
 
 
-# ----------------------------------------------------------------------------- type III
-def _vo_products(v, o, H, KV, r):
-    grp = H // KV
-    return [np.asarray(o[:, q * r:(q + 1) * r], np.float64) @ np.asarray(v[(q // grp) * r:(q // grp + 1) * r], np.float64)
-            for q in range(H)]
+# type III (V/O): tests/test_gpu_type3.py
 
 
-def test_type3_against_reference_golden(ops, golden):
-    """compress_head (MHA) and compress_head_grouped (GQA) outputs of the reference itself."""
-    g = golden("vo")
-    hd, r = int(g["hd"]), int(g["rank"])
-    c = torch.tensor(g["c"], device=DEV, dtype=torch.float32)
-    wv = torch.tensor(g["mha_wv"], device=DEV).bfloat16()
-    wo = torch.tensor(g["mha_wo"], device=DEV).bfloat16()
-    v, o = ops.vo_compress(c, float(g["ridge"]), wv, wo, 2, 2, hd, r)
-    ours = _vo_products(v.float().cpu().numpy(), o.float().cpu().numpy(), 2, 2, r)
-    want = _vo_products(g["mha_v"], g["mha_o"], 2, 2, r)
-    for a, b in zip(ours, want):
-        assert rel(a, b) < 5e-3          # both factors are bf16-rounded on our side
-    v, o = ops.vo_compress(c, float(g["ridge"]), wv[:hd].contiguous(), wo, 2, 1, hd, r)
-    ours = _vo_products(v.float().cpu().numpy(), o.float().cpu().numpy(), 2, 1, r)
-    want = _vo_products(g["gqa_v"], g["gqa_o"], 2, 1, r)
-    for a, b in zip(ours, want):
-        assert rel(a, b) < 5e-3
-
-
-@pytest.mark.parametrize("d,H,KV,hd,r", [(256, 4, 4, 64, 40), (512, 8, 2, 64, 48), (512, 4, 4, 128, 96),
-                                         (384, 6, 3, 32, 20), (256, 2, 2, 128, 128)])
-def test_type3_matches_oracle(ops, d, H, KV, hd, r):
-    x = shaped(4 * d, d, seed=d + hd, spread=0.6).double().numpy()
-    c = torch.tensor(x.T @ x / x.shape[0], device=DEV, dtype=torch.float32)
-    g = torch.Generator().manual_seed(d)
-    wv = (torch.randn(KV * hd, d, generator=g) * 0.05).bfloat16()
-    wo = (torch.randn(d, H * hd, generator=g) * 0.05).bfloat16()
-    v, o = ops.vo_compress(c, 1e-5, wv.to(DEV), wo.to(DEV), H, KV, hd, r)
-    _, v64, o64 = O.vo_layer(wv.float().numpy(), wo.float().numpy(), c.double().cpu().numpy(), H, KV, hd, r, 1e-5)
-    assert v.shape == (KV * r, d) and o.shape == (d, H * r)
-    ours = _vo_products(v.float().cpu().numpy(), o.float().cpu().numpy(), H, KV, r)
-    want = _vo_products(O.to_bf16(v64), O.to_bf16(o64), H, KV, r)
-    exact = _vo_products(v64, o64, H, KV, r)
-    for a, b, e in zip(ours, want, exact):
-        # sign-free comparison: O'V' per head is unique.  The bound is the error the reference's own
-        # bf16 rounding of the two factors makes against exact arithmetic.
-        assert rel(a, e) < 1.5 * rel(b, e) + 1e-4
-    # sign-aligned factors, element-wise
-    grp = H // KV
-    for h in range(KV):
-        vo, vr = v.float().cpu().numpy()[h * r:(h + 1) * r], v64[h * r:(h + 1) * r]
-        sgn = np.sign(np.sum(vo * vr, axis=1))
-        assert rel(vo * sgn[:, None], vr) < 5e-3
+def test_pack_unpack_upper_round_trip(ops):
+    """Wire format of the cross-rank reduction: row-major packed upper triangle, exact copy."""
+    for n in (1, 7, 64, 300, 1096):
+        g = torch.Generator().manual_seed(n)
+        c = torch.randn(n, n + 3, generator=g).to(DEV)[:, :n]           # strided view (ld > n)
+        packed = torch.full((ops.packed_upper_numel(n) + 5,), -7.0, device=DEV)
+        ops.pack_upper_(packed, c)
+        iu = torch.triu_indices(n, n, device=DEV)
+        assert torch.equal(packed[:-5], c[iu[0], iu[1]])
+        assert torch.all(packed[-5:] == -7.0)
+        out = torch.full((n, n), 3.0, device=DEV)
+        ops.unpack_upper_(out, packed)
+        assert torch.equal(torch.triu(out), torch.triu(c))
+        assert torch.all(torch.tril(out, -1) == torch.tril(torch.full((n, n), 3.0, device=DEV), -1))
 
 
 # ----------------------------------------------------------------------------- lanes / rasterisation

@@ -107,13 +107,18 @@ def test_pipeline_matches_reference(golden, tmp_path, tag):
         assert rel(ours[(l, "mlp")]["down"].float().cpu().numpy(), g[f"L{l}_mlp_down"]) < 2e-3
         for k in ("q_proj", "k_proj"):
             assert torch.equal(ours[(l, "qk")][k], ref_layers[(l, "qk")][k])
+        # V/O: singular vectors are defined up to sign — align each component with the reference's,
+        # then the bf16 tensors must agree like type-I's (1e-3 and > 97 % identical elements)
         r = g[f"L{l}_vo_v_proj"].shape[0] // KV
         vo, vr = ours[(l, "vo")], ref_layers[(l, "vo")]
-        for q in range(H):
-            h = q // (H // KV)
-            po = vo["o_proj"][:, q * r:(q + 1) * r].double() @ vo["v_proj"][h * r:(h + 1) * r].double()
-            pr = vr["o_proj"][:, q * r:(q + 1) * r].double() @ vr["v_proj"][h * r:(h + 1) * r].double()
-            assert rel(po.cpu().numpy(), pr.cpu().numpy()) < 1e-2
+        v_o, v_r = vo["v_proj"].double(), vr["v_proj"].double()
+        sgn = torch.sign((v_o * v_r).sum(1))
+        sgn_o = sgn.view(KV, r).repeat_interleave(H // KV, dim=0).reshape(-1)
+        v_a, o_a = v_o * sgn[:, None], vo["o_proj"].double() * sgn_o[None, :]
+        o_r = vr["o_proj"].double()
+        assert rel(v_a.cpu().numpy(), v_r.cpu().numpy()) < 1e-3
+        assert rel(o_a.cpu().numpy(), o_r.cpu().numpy()) < 1e-3
+        assert (v_a == v_r).double().mean() > 0.97 and (o_a == o_r).double().mean() > 0.97
 
     # perplexity of the rebuilt model: ours vs the reference's tensors through the same class
     ppl_ours = compressed_ppl(adapter, tmp_path, ours, masks, "ours")
@@ -228,28 +233,6 @@ def test_full_rank_roundtrip_preserves_the_model(tmp_path, preset, monkeypatch):
     assert err < 5e-2, err
 
 
-def test_type1_workers_do_not_change_results(golden, tmp_path):
-    """compress_nystrom with two worker threads (two streams, two lane sets) produces the same
-    layer tensors as the single-threaded loop."""
-    from modegpt_b200.compression.compress_mlp import compress_nystrom
-
-    g = golden("pipeline_llama_gqa")
-    L = int(g["cfg"][2])
-    f32 = lambda k: torch.tensor(g[k], device=DEV, dtype=torch.float32)
-    keep = [float(x) for x in g["keep"]]
-    out = {}
-    for workers in (1, 2):
-        adapter = make_adapter(g, tmp_path, keep_layers_in_memory=True, mlp_workers=workers)
-        compress_nystrom(adapter, [f32(f"cov_mlp{l}") for l in range(L)], keep, list(range(L)))
-        torch.cuda.synchronize()
-        out[workers] = dict(adapter._layer_store)
-    assert set(out[1]) == set(out[2]) == {(l, "mlp") for l in range(L)}
-    for key in out[1]:
-        for name in ("up", "gate"):
-            assert torch.equal(out[1][key][name], out[2][key][name])
-        assert rel(out[2][key]["down"].float().cpu().numpy(), out[1][key]["down"].float().cpu().numpy()) < 2e-3
-
-
 def test_type3_grouped_layers_match_one_at_a_time(golden, tmp_path):
     """compress_vo in groups (mg_vo_prepare back to back, mg_vo_finish on one stream per layer) is
     the same computation as one mg_vo_compress per layer: bit-identical tensors."""
@@ -270,3 +253,76 @@ def test_type3_grouped_layers_match_one_at_a_time(golden, tmp_path):
         for key in out[1]:
             for name in ("v_proj", "o_proj"):
                 assert torch.equal(out[1][key][name], out[group][key][name])
+
+
+def test_opt_pipeline_matches_oracle_fixture(golden, tmp_path):
+    """BASELINE config #1 (OPT) in miniature against tests/golden/pipeline_opt.npz — the oracle-level
+    OPT pipeline (oracle/opt_pipeline.py: statistics on relu(fc1), per-head C_q / C_k incl. biases,
+    C_x from self_attn_layer_norm, compress_head_opt, MHA compress_head, bias handling), whose
+    per-head pieces make_golden.py cross-checked against the reference's own functions."""
+    from transformers import AutoModelForCausalLM, OPTConfig
+
+    from modegpt_b200.adapters.CompressionConfig import CompressionConfig
+    from modegpt_b200.adapters.model_adapter import ModelAdapter
+    from modegpt_b200.calibration import load_calibs
+    from modegpt_b200.compression.compress_mlp import compress_nystrom
+    from modegpt_b200.compression.compress_qk import compress_qk
+    from modegpt_b200.compression.compress_vo import compress_vo
+    from modegpt_b200.compression_utils import allocate_global_sparsity
+    from oracle import modegpt_oracle as O
+
+    g = golden("pipeline_opt")
+    d, ffn, L, H, _, hd, vocab = (int(x) for x in g["cfg"])
+    ratio, ridge, ridge_vo, smooth, cap = (float(x) for x in g["hyper"])
+    cfg = OPTConfig(hidden_size=d, num_attention_heads=H, ffn_dim=ffn, num_hidden_layers=L, vocab_size=vocab,
+                    max_position_embeddings=256, word_embed_proj_dim=d, do_layer_norm_before=True)
+    model = AutoModelForCausalLM.from_config(cfg)
+    model.load_state_dict({k[2:]: torch.tensor(v) for k, v in g.items() if k.startswith("w:")})
+    model = model.to(torch.bfloat16).to(DEV).eval()
+    adapter = ModelAdapter.from_model(model, tokenizer=None)
+    adapter.config = CompressionConfig(
+        model="tiny-opt", temp_storage_dir=str(tmp_path / "layers"), output_dir=str(tmp_path / "out"),
+        order="mlp,qk,vo", calib_size=4, calibs_batch_size=2, compression_ratio=ratio, max_sparsity=cap,
+        sparsity_smoothing=smooth, ridge_vo=ridge_vo, ridge_qk=1e-2, nystrom_ridge=ridge, dataset="synthetic",
+        seq_len=96, eval_samples=8, keep_layers_in_memory=True)
+    tokens = torch.tensor(g["tokens"], device=DEV)
+    adapter.calibs = [tokens[0:2], tokens[2:4]]
+    layers = list(range(L))
+    cov_mlp, cov_q, cov_k, cov_x, bi = load_calibs(adapter, 4, 2, dataset="synthetic", target_layers=layers)
+    # GPU forward vs the fixture's CPU forward: bf16 noise only
+    for l in layers:
+        assert rel(cov_mlp[l].cpu().numpy(), g[f"cov_mlp{l}"]) < 3e-2
+        assert rel(cov_x[l].cpu().numpy(), g[f"cov_x{l}"]) < 3e-2
+        assert rel(cov_q[l].cpu().numpy(), g[f"cov_q{l}"]) < 3e-2
+        assert rel(cov_k[l].cpu().numpy(), g[f"cov_k{l}"]) < 3e-2
+    np.testing.assert_allclose(bi, g["bi"], rtol=2e-2)
+
+    # decompositions on the fixture's statistics
+    f32 = lambda k: torch.tensor(g[k], device=DEV, dtype=torch.float32)
+    keep = allocate_global_sparsity(list(map(float, g["bi"])), ratio, smooth, cap, adapter=adapter)
+    np.testing.assert_allclose(keep, g["keep"], rtol=0, atol=1e-12)
+    compress_nystrom(adapter, [f32(f"cov_mlp{l}") for l in layers], keep, layers)
+    compress_qk(adapter, ([f32(f"cov_q{l}") for l in layers], [f32(f"cov_k{l}") for l in layers]), keep,
+                target_layers=layers)
+    compress_vo(adapter, [f32(f"cov_x{l}") for l in layers], keep, target_layers=layers)
+    ours = dict(adapter._layer_store)
+    bf = lambda t: t.float().cpu().numpy()
+    for l in layers:
+        r_mlp, r_qk, r_vo = (int(x) for x in g[f"L{l}_ranks"])
+        mlp, qk, vo = ours[(l, "mlp")], ours[(l, "qk")], ours[(l, "vo")]
+        np.testing.assert_array_equal(bf(mlp["up"]), g[f"L{l}_mlp_up"])              # same rows kept
+        np.testing.assert_array_equal(bf(mlp["up_bias"]), g[f"L{l}_mlp_up_bias"])
+        np.testing.assert_array_equal(bf(mlp["down_bias"]), g[f"L{l}_mlp_down_bias"])
+        assert rel(bf(mlp["down"]), g[f"L{l}_mlp_down"]) < 2e-3
+        np.testing.assert_array_equal(bf(qk["q_proj"]), g[f"L{l}_qk_q_proj"])
+        np.testing.assert_array_equal(bf(qk["k_proj"]), g[f"L{l}_qk_k_proj"])
+        np.testing.assert_array_equal(bf(qk["q_bias"]), g[f"L{l}_qk_q_bias"])
+        np.testing.assert_array_equal(bf(qk["k_bias"]), g[f"L{l}_qk_k_bias"])
+        v64, o64 = g[f"L{l}_vo_v64"], g[f"L{l}_vo_o64"]
+        vb, ob = bf(vo["v_proj"]).astype(np.float64), bf(vo["o_proj"]).astype(np.float64)
+        assert vb.shape == (H * r_vo, d)
+        sgn = np.sign(np.sum(vb * v64, axis=1))
+        assert rel(vb * sgn[:, None], O.to_bf16(v64)) < 1e-3
+        assert rel(ob * sgn[None, :], O.to_bf16(o64)) < 1e-3
+        assert np.mean(vb * sgn[:, None] == O.to_bf16(v64)) > 0.97
+        np.testing.assert_allclose(bf(vo["o_bias"]), g[f"L{l}_vo_o_bias"], rtol=2e-2, atol=2e-3)

@@ -84,6 +84,24 @@ def test_vo_heads(golden):
     assert rel(o * np.tile(sgn, 2)[None, :], g["gqa_o"]) < 1e-8
 
 
+def test_vo_heads_ill_conditioned(golden):
+    """channel spread 1.5: cond(C) ~ 7e6, sigma_1 / sigma_r ~ 27 — the fixture that separates an
+    fp32 Gram-squaring type-III from a factor-based one (tests/test_gpu_kernels.py)."""
+    g = golden("vo_illcond")
+    assert float(g["cond_c"]) > 1e6
+    hd, rank, heads = int(g["hd"]), int(g["rank"]), int(g["heads"])
+    c = g["c"].astype(np.float64)
+    _, v64, o64 = O.vo_layer(g["wv"], g["wo"], c, heads, heads, hd, rank, float(g["ridge"]))
+    sgn = np.sign(np.sum(v64 * g["mha_v"], axis=1))
+    assert rel(v64 * sgn[:, None], g["mha_v"]) < 1e-7
+    assert rel(o64 * sgn[None, :], g["mha_o"]) < 1e-7
+    _, v64, o64 = O.vo_layer(g["wv"][:2 * hd], g["wo"], c, heads, 2, hd, rank, float(g["ridge"]))
+    sgn = np.sign(np.sum(v64 * g["gqa_v"], axis=1))
+    assert rel(v64 * sgn[:, None], g["gqa_v"]) < 1e-7
+    sgn_o = np.repeat(sgn.reshape(2, rank), 2, axis=0).reshape(-1)
+    assert rel(o64 * sgn_o[None, :], g["gqa_o"]) < 1e-7
+
+
 @pytest.mark.parametrize("tag", ["llama_mha", "llama_gqa", "qwen3_gqa"])
 def test_pipeline(golden, tag):
     """Layer-level functions and the statistics, on the recorded hook inputs of a tiny model."""
@@ -138,3 +156,35 @@ def test_pipeline(golden, tag):
                 prod_ref = orf.astype(np.float64) @ vr.astype(np.float64)
                 prod = o64[:, q * rv:(q + 1) * rv] @ vo_h
                 assert rel(prod, prod_ref) < 2e-2   # reference side is bf16-rounded
+
+
+def test_pipeline_opt(golden):
+    """BASELINE config #1 in miniature: the oracle-level OPT pipeline (oracle/opt_pipeline.py) on
+    the recorded tiny OPT reproduces the fixture (which make_golden.py cross-checked, head by head,
+    against the reference's surviving compress_head_opt / compress_head / get_ridge_scores)."""
+    import torch
+    from transformers import AutoModelForCausalLM, OPTConfig
+
+    from oracle import opt_pipeline
+
+    g = golden("pipeline_opt")
+    d, ffn, L, H, _, hd, vocab = (int(x) for x in g["cfg"])
+    cfg = OPTConfig(hidden_size=d, num_attention_heads=H, ffn_dim=ffn, num_hidden_layers=L, vocab_size=vocab,
+                    max_position_embeddings=256, word_embed_proj_dim=d, do_layer_norm_before=True)
+    model = AutoModelForCausalLM.from_config(cfg)
+    model.load_state_dict({k[2:]: torch.tensor(v) for k, v in g.items() if k.startswith("w:")})
+    model = model.to(torch.bfloat16).eval()
+    tokens = torch.tensor(g["tokens"])
+    ratio, ridge, ridge_vo, smooth, cap = (float(x) for x in g["hyper"])
+    res = opt_pipeline.run(model, [tokens[0:2], tokens[2:4]], compression_ratio=ratio, nystrom_ridge=ridge,
+                           ridge_vo=ridge_vo, smoothing=smooth, max_sparsity=cap)
+    np.testing.assert_allclose(res["bi"], g["bi"], rtol=1e-9)
+    np.testing.assert_allclose(res["keep"], g["keep"], rtol=0, atol=1e-12)
+    for l in range(L):
+        assert rel(res[f"cov_mlp{l}"], g[f"cov_mlp{l}"]) < 1e-12
+        np.testing.assert_array_equal(res[f"L{l}_mlp_idx"], g[f"L{l}_mlp_idx"])
+        np.testing.assert_array_equal(res[f"L{l}_qk_mask"], g[f"L{l}_qk_mask"])
+        np.testing.assert_array_equal(res[f"L{l}_qk_q_bias"], g[f"L{l}_qk_q_bias"])
+        assert (res[f"L{l}_mlp_down"] == g[f"L{l}_mlp_down"]).mean() > 0.99
+        sgn = np.sign(np.sum(res[f"L{l}_vo_v64"] * g[f"L{l}_vo_v64"], axis=1))
+        assert rel(res[f"L{l}_vo_v64"] * sgn[:, None], g[f"L{l}_vo_v64"]) < 1e-7

@@ -11,7 +11,7 @@ wv = [(torch.randn(KV * hd, d, device=dev) * 0.02).bfloat16() for _ in range(4)]
 wo = [(torch.randn(d, H * hd, device=dev) * 0.02).bfloat16() for _ in range(4)]
 streams = [torch.cuda.Stream() for _ in range(4)]
 def run(parallel):
-    ws = [ops.vo_prepare(cx, 1e-5, wv[i], wo[i], H, KV, hd) for i in range(4)]
+    ws = [ops.vo_prepare(cx, 1e-5, wv[i], wo[i], H, KV, hd)[0] for i in range(4)]
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for i in range(4):
         if parallel:
