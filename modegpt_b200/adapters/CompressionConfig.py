@@ -44,6 +44,8 @@ class CompressionConfig:
     sync_save: bool = False               # blocking torch.save per layer, as the reference does
     stream_layers: bool = False           # layer-streamed calibration: one layer's statistics at a time
     eager_forward: bool = False           # keep HF's eager elementwise kernels in the calibration forward
+    skip_rebuild: bool = False            # stop after the layer files are written (no convert / save / reload / ppl)
+    skip_baseline_ppl: bool = False       # do not evaluate the uncompressed model first
 
     _HELP: typing.ClassVar[dict] = {
         "order": "mlp,qk,vo  -- <method>,<method>,<method>",

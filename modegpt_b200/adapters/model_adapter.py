@@ -385,8 +385,14 @@ class ModelAdapter(ABC):
         self._writer.submit(path, weights)
         first = next(iter(weights.values()))
         if first.is_cuda:
-            free, total = torch.cuda.mem_get_info(first.device)
-            if free > 0.3 * total:
+            # cudaMemGetInfo takes the driver's context lock — behind the writer threads' copies it
+            # cost ~10 ms per call (96 calls on a 7B run): ask once every 16 saves
+            self._cache_probe = getattr(self, "_cache_probe", 0)
+            if self._cache_probe % 16 == 0:
+                free, total = torch.cuda.mem_get_info(first.device)
+                self._cache_ok = free > 0.3 * total
+            self._cache_probe += 1
+            if self._cache_ok:
                 self._layer_cache[(int(layer_idx), suffix)] = weights
 
     def prepare_writer(self) -> None:
@@ -395,7 +401,10 @@ class ModelAdapter(ABC):
             return
         from ..handoff import LayerWriter
 
-        self._writer = LayerWriter(device=next(self.model.parameters()).device)
+        # one pool buffer holds the largest tensor a layer can produce (an uncompressed MLP matrix)
+        largest = 2 * self.d_model * max(self.get_n_inner(), self.n_heads * self.head_dim)
+        self._writer = LayerWriter(device=next(self.model.parameters()).device,
+                                   pool_buffer_bytes=(largest + 4095) // 4096 * 4096)
 
     def flush_saves(self) -> None:
         """Block until every submitted layer file is on disk (raises if a write failed)."""

@@ -74,6 +74,7 @@ struct NystromWs {
   bf16* z_planes;   // [3][128 x dp]      X planes of one panel (single-stream back-substitution)
   bf16* zb_planes;  // [3][4*128 x dp]    forward substitution: Z planes of one outer block
   bf16* xb_planes;  // [2][3][4*128 x dp] back-substitution: X planes of an outer block (double-buffered)
+  uint8_t* kept;    // [n]                1 where the channel is in idx
   mg::CholWorkspace chol;
   size_t bytes;
 };
@@ -90,6 +91,7 @@ NystromWs carve_nystrom(void* p, int64_t n, int64_t k, int64_t d) {
   w.z_planes = c.take<bf16>(kPlanes * kNB * dp);        // single-stream path only
   w.zb_planes = c.take<bf16>(kPlanes * 4 * kNB * dp);
   w.xb_planes = c.take<bf16>(2 * kPlanes * 4 * kNB * dp);
+  w.kept = c.take<uint8_t>(n);
   w.chol.u_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.l_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
@@ -165,19 +167,27 @@ __global__ void __launch_bounds__(256) gather_sym_kernel(const float* __restrict
   }
 }
 
-// planes_p[l, i] = p-th plane of C[l, idx_i]   for l in [0, n), i in [0, k)
+__global__ void mark_kept_kernel(const int64_t* __restrict__ idx, int64_t k, uint8_t* __restrict__ kept) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < k) kept[idx[i]] = 1;
+}
+
+// planes_p[l, i] = p-th plane of C[l, idx_i]   for l in [0, n), i in [0, k); rows l that are
+// themselves kept are written as ZERO (the correction form of the Nystrom solve, see the driver)
 __global__ void __launch_bounds__(256) gather_cols_planes_kernel(const float* __restrict__ C,
                                                                  int64_t ldc, int64_t n,
                                                                  const int64_t* __restrict__ idx,
                                                                  int64_t k,
+                                                                 const uint8_t* __restrict__ kept,
                                                                  bf16* __restrict__ planes,
                                                                  int64_t ldp, int64_t pstride) {
   const int64_t l = blockIdx.y;
   const float* row = C + l * ldc;
+  const bool skip = kept[l] != 0;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < k;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     bf16 h, m, lo;
-    split3(__ldg(row + idx[i]), h, m, lo);
+    split3(skip ? 0.f : __ldg(row + idx[i]), h, m, lo);
     const int64_t o = l * ldp + i;
     planes[o] = h;
     planes[pstride + o] = m;
@@ -203,6 +213,38 @@ __global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const IN* __rest
   for (int i = ty; i < 32; i += 8) {
     const int64_t orow = c0 + i, ocol = r0 + tx;
     if (orow < cols && ocol < rows) out[orow * ld_out + ocol] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// rhs[i, c] -= jitter * Wd^T[idx_i, c]   (wdt = W_down^T, bf16 [n x ldw])
+__global__ void __launch_bounds__(256) sub_jitter_rows_kernel(float* __restrict__ rhs, int64_t ldr,
+                                                              const bf16* __restrict__ wdt, int64_t ldw,
+                                                              const int64_t* __restrict__ idx, int64_t d,
+                                                              float jitter) {
+  const int64_t i = blockIdx.x;
+  const bf16* src = wdt + idx[i] * ldw;
+  float* dst = rhs + i * ldr;
+  for (int64_t c = threadIdx.x; c < d; c += blockDim.x)
+    dst[c] = fmaf(-jitter, __bfloat162float(src[c]), dst[c]);
+}
+
+// out[c, i] = bf16(X[i, c] + Wd^T[idx_i, c]):  W_down' = W_down[:, idx] + correction, transposed store
+__global__ void __launch_bounds__(256) add_kept_transpose_kernel(const float* __restrict__ x, int64_t ldx,
+                                                                 const bf16* __restrict__ wdt, int64_t ldw,
+                                                                 const int64_t* __restrict__ idx,
+                                                                 int64_t k, int64_t d,
+                                                                 bf16* __restrict__ out, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;      // r: kept-channel index i, c: output feature
+    tile[i][tx] = (r < k && c < d) ? x[r * ldx + c] + __bfloat162float(wdt[idx[r] * ldw + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t orow = c0 + i, ocol = r0 + tx;
+    if (orow < d && ocol < k) out[orow * ld_out + ocol] = __float2bfloat16_rn(tile[tx][i]);
   }
 }
 
@@ -479,11 +521,20 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   mg::LaneScope scope(s, k);
   const mg::Lanes& L = scope.lanes();
 
-  // tri lane: operands of the cross term  rhs[k, d] = C[idx, :] W_down^T = (C[:, idx])^T (W_down^T)
+  // Correction form.  With A = C_kk + jitter I and the columns of C split into kept / dropped,
+  //     A^-1 C[idx, :] W_d^T = W_d[:, idx]^T + A^-1 (C[idx, dropped] W_d[:, dropped]^T - jitter W_d[:, idx]^T)
+  // because A^-1 C_kk = I - jitter A^-1.  The kept channels' own contribution — the large,
+  // exactly-cancelling part when "massive activation" channels are kept — never passes through
+  // the fp32 right-hand side or the fp32 solve: only the correction does (measured on a statistic
+  // with a 1e6 diagonal spread and equilibrated cond 3.5e4: 2e-2 -> 1e-5 relative error).
+  // tri lane: operands of the cross term  rhs[k, d] = C[idx, dropped] W_down[:, dropped]^T
   // — independent of the factorisation of C_kk, which starts at once on the chain lane
+  cudaMemsetAsync(w.kept, 0, static_cast<size_t>(n), L.tri);
+  mark_kept_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, L.tri>>>(idx, k, w.kept);
+  if ((rc = cuda_rc())) return rc;
   gather_cols_planes_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
                                    static_cast<unsigned>(n)),
-                              256, 0, L.tri>>>(C, ldc, n, idx, k, w.g_planes, kp, n * kp);
+                              256, 0, L.tri>>>(C, ldc, n, idx, k, w.kept, w.g_planes, kp, n * kp);
   if ((rc = cuda_rc())) return rc;
   transpose_to_bf16_kernel<bf16><<<dim3(static_cast<unsigned>((n + 31) / 32),
                                         static_cast<unsigned>((d + 31) / 32)),
@@ -515,6 +566,8 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
     g.max_ctas = L.bulk_cta_cap();
     MG_TIMED(L.tri, "nystrom.cross_term", rc = mg::gemm_tn_launch(g, L.tri));
     if (rc) return rc;
+    sub_jitter_rows_kernel<<<static_cast<unsigned>(k), 256, 0, L.tri>>>(w.rhs, dp, w.wdt, dp, idx, d, jitter);
+    if ((rc = cuda_rc())) return rc;
   }
   // chain lane: C_kk + jitter I and its Cholesky factor (planes of U and of L = U^T)
   gather_sym_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
@@ -708,10 +761,13 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
       if (rc) return rc;
     }
   }
-  // ---- W_down' [d, k] = X^T, bf16
-  transpose_to_bf16_kernel<float><<<dim3(static_cast<unsigned>((d + 31) / 32),
-                                         static_cast<unsigned>((k + 31) / 32)),
-                                    256, 0, L.chain>>>(w.rhs, dp, k, d, static_cast<bf16*>(Wd_out), ld_out);
+  // ---- W_down' [d, k] = (W_down[:, idx]^T + X)^T, bf16
+  L.record(L.misc[0], L.tri);      // wdt was produced on the tri lane
+  L.wait(L.chain, L.misc[0]);
+  add_kept_transpose_kernel<<<dim3(static_cast<unsigned>((d + 31) / 32),
+                                   static_cast<unsigned>((k + 31) / 32)),
+                              256, 0, L.chain>>>(w.rhs, dp, w.wdt, dp, idx, k, d,
+                                                 static_cast<bf16*>(Wd_out), ld_out);
   rc = cuda_rc();
   mg::Prof::get().report(s, "mg_nystrom_down_f32");
   return rc;

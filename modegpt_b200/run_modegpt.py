@@ -82,10 +82,11 @@ def main(trial=None, config: CompressionConfig | None = None):
     adapter.metrics["note"] = config.note
 
     # held-out sequences are dealt to the ranks, the NLL sum is all-reduced (eval.compute_perplexity)
-    baseline = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
-    if is_root:
-        logger.info(f"Baseline ppl: {baseline}")
-    adapter.metrics["baseline-ppl"] = baseline
+    if not config.skip_baseline_ppl:
+        baseline = compute_perplexity(model, tokenizer, dataset=config.dataset, adapter=adapter)
+        if is_root:
+            logger.info(f"Baseline ppl: {baseline}")
+        adapter.metrics["baseline-ppl"] = baseline
 
     adapter.prepare_writer()      # writer threads + 384 MB of pinned bounce buffers, before the timed stages
     n_layers = adapter.n_layers
@@ -167,6 +168,16 @@ def main(trial=None, config: CompressionConfig | None = None):
     adapter.metrics.update({**timings, "calib_tokens_per_s": tokens / max(timings["calibration_s"], 1e-9),
                             "compress_s_per_layer": (compress_wall + timings["file_flush_s"]) / n_layers,
                             "world_size": D.world_size()})
+    if is_root:
+        logger.info(f"calibration {timings['calibration_s']:.2f}s "
+                    f"({adapter.metrics['calib_tokens_per_s']:.0f} tok/s), stages: mlp {timings['mlp_s']:.2f}s "
+                    f"qk {timings['qk_s']:.2f}s vo {timings['vo_s']:.2f}s + file flush "
+                    f"{timings['file_flush_s']:.2f}s -> compress {adapter.metrics['compress_s_per_layer']:.3f} "
+                    f"s/layer (max over ranks is the slowest rank's line above)")
+    if config.skip_rebuild:
+        if is_root:
+            adapter.save_metrics()
+        return None
     if is_root:
         suffixes = [s for s in ("mlp", "qk", "vo") if s in config.order]
         adapter.convert_model(saved_layers_dir=config.temp_storage_dir, suffixes=suffixes)

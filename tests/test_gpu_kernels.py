@@ -188,6 +188,36 @@ def test_type1_matches_oracle(ops, n, d, keep, ridge, spread):
         _bf16_close(down, want["down"])
 
 
+def test_type1_graded_statistic_with_massive_channels(ops):
+    """Nystrom solve on a statistic with a 1e6 diagonal spread (channels scaled 1e-1.5 .. 1e1.5 plus
+    a few 'massive activation' channels at 1e3) and correlated channels: cond(C_kk + 1e-6 I) > 1e9.
+    Cholesky's rounding errors are invariant under diagonal scaling, so what matters is the
+    conditioning of the EQUILIBRATED matrix, not the raw spread — the fp32 factorisation must
+    reproduce the fp64 oracle's bf16 result to 1e-3 (the jitter itself is below an fp32 ulp of the
+    large diagonal entries; the oracle adds it exactly)."""
+    n, d, keep, ridge = 1024, 192, 0.75, 1e-4
+    g = torch.Generator().manual_seed(5)
+    scale = 10.0 ** (3.0 * torch.rand(n, generator=g) - 1.5)
+    scale[torch.randperm(n, generator=g)[:6]] = 1e3
+    base = torch.randn(4 * n, n, generator=g)
+    mix = torch.eye(n) + 0.3 * torch.randn(n, 24, generator=g) @ torch.randn(24, n, generator=g) / 24 ** 0.5
+    x = ((base @ mix) * scale).double().numpy()
+    c = torch.tensor(x.T @ x / x.shape[0], device=DEV, dtype=torch.float32)
+    c64 = c.double().cpu().numpy()
+    diag = np.diag(c64)
+    assert diag.max() / diag.min() > 1e6
+    wu = (torch.randn(n, d, generator=g) * 0.05).bfloat16()
+    wd = (torch.randn(d, n, generator=g) * 0.05).bfloat16()
+    want, ref_idx, rank = O.nystrom_mlp(wu.float().numpy(), None, wd.float().numpy(), c64, keep, ridge)
+    ckk = c64[np.ix_(ref_idx, ref_idx)] + 1e-6 * np.eye(rank)
+    assert np.linalg.cond(ckk) > 1e9
+    scores = ops.ridge_scores(c, float(np.float32(ridge)))
+    idx = ops.select_k(scores, rank)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)
+    # 1e-3 holds; the share of bf16 roundings that flip is a little above type-I's usual 3 % here
+    _bf16_close(ops.nystrom_down(c, idx, wd.to(DEV)), want["down"], frac=0.94)
+
+
 def test_select_k_edge_cases(ops):
     s = torch.tensor([3.0, 1.0, 2.0, 1.0, 5.0, 1.0, -2.0, 0.0], device=DEV)
     assert ops.select_k(s, 3).tolist() == [1, 6, 7]                 # ties resolve to the lower index

@@ -75,7 +75,7 @@ def main():
                 if suf != "vo" and name != "down":
                     assert torch.equal(t, ref), (l, suf, name)     # gathers: bit-exact
                 else:
-                    assert rel(t, ref) < 5e-3, (l, suf, name, rel(t, ref))
+                    assert rel(t, ref) < 1e-3, (l, suf, name, rel(t, ref))
     assert worst < 1e-5, worst
     assert max(abs(a - b) for a, b in zip(keep_d, keep_s)) < 1e-6
     assert len(masks_d) == adapter.n_layers
