@@ -79,6 +79,13 @@ int mg_unpack_upper_f32(const float* packed, int64_t n, float* C, int64_t ldc, v
 
 /* ---- type-I: Nystrom MLP ---------------------------------------------------------------------- */
 
+/* Tell the library how many type-I factorisations the caller runs side by side (host threads with
+ * one stream each; the library has one set of internal lanes per concurrent call, up to 2).  The
+ * persistent bulk GEMMs of each factorisation are then capped at 1/n of the SMs left after the
+ * chain reserve, so a second factorisation's panel chain is never starved by the first one's
+ * trailing updates.  Process-wide; default 1.  Results do not depend on it. */
+int mg_set_concurrent_factorizations(int n);
+
 /* scores[j] = diag((C + ridge I)^-1)_j.  C: fp32 [n,n], upper triangle read.  Two-level blocked
  * Cholesky (fp64 128-wide diagonal blocks, fused triangular-solve panels, tcgen05 updates on bf16x3
  * planes: K = 128 inside an outer block of 4 panels, K = 512 below it) and a blocked triangular

@@ -29,6 +29,7 @@ SIGNATURES: dict[str, tuple] = {
     "mg_scale_f32": (i32, [vp, i64, f32, vp]),
     "mg_pack_upper_f32": (i32, [vp, i64, i64, vp, vp]),
     "mg_unpack_upper_f32": (i32, [vp, i64, vp, i64, vp]),
+    "mg_set_concurrent_factorizations": (i32, [i32]),
     "mg_ridge_scores_ws_bytes": (C.c_size_t, [i64]),
     "mg_ridge_scores_f32": (i32, [vp, i64, i64, f32, vp, vp, C.c_size_t, vp, vp]),
     "mg_select_k_f32": (i32, [vp, i64, i64, i32, vp, vp]),

@@ -70,7 +70,70 @@ def _compress_layer(adapter: ModelAdapter, cov, keep_ratios, layer_idx: int) -> 
 def compress_nystrom(adapter: ModelAdapter, cov, keep_ratios, target_layers, ridge_lambda=1e-4):
     """Layer loop + `save_layer(suffix="mlp")` (compress_mlp.py:67-117).  As in the reference the
     ridge actually used is `adapter.config.nystrom_ridge` (:93).  Each rank takes the layers it
-    owns (`distributed.owned_layers`); inside a layer the library spreads the factorisation over
-    its own lanes, so one host thread keeps the GPU busy."""
-    for layer_idx in D.owned_layers(target_layers):
-        _compress_layer(adapter, cov, keep_ratios, layer_idx)
+    owns (`distributed.owned_layers`).
+
+    A factorisation is bound by its panel chain (about 12 ms of tensor work spread over 21 ms), so
+    layers — which are independent — are decomposed `config.mlp_workers` at a time: that many host
+    threads, each with its own CUDA stream and, inside the library, its own set of lanes, take
+    layers from a shared list.  `mg_set_concurrent_factorizations` divides the SMs left after the
+    chain reserve between their bulk GEMMs: in round 1 two workers gained nothing because one
+    factorisation's persistent trailing updates filled the GPU and the other's chain kernels
+    queued behind them.  Results do not depend on the number of workers."""
+    from .._lib import lib
+
+    layers = list(D.owned_layers(target_layers))
+    workers = max(1, min(int(getattr(adapter.config, "mlp_workers", 1)), len(layers)))
+    if workers == 1 or not layers or not cov[layers[0]].is_cuda:
+        for layer_idx in layers:
+            _compress_layer(adapter, cov, keep_ratios, layer_idx)
+        return
+
+    import threading
+
+    adapter.prepare_writer()                # created once, before the workers race for it
+    device = cov[layers[0]].device
+    caller = torch.cuda.current_stream(device)
+    ready = torch.cuda.Event()
+    ready.record(caller)
+    pending = list(reversed(layers))        # pop() hands layers out in ascending order
+    lock = threading.Lock()
+    errors: list[BaseException] = []
+    streams = _worker_streams(device, workers)
+
+    def work(stream):
+        try:
+            torch.cuda.set_device(device)
+            with torch.no_grad(), torch.cuda.stream(stream):
+                stream.wait_event(ready)     # statistics / weights produced on the caller's stream
+                while not errors:
+                    with lock:
+                        if not pending:
+                            break
+                        layer_idx = pending.pop()
+                    _compress_layer(adapter, cov, keep_ratios, layer_idx)
+        except BaseException as e:           # re-raised on the calling thread
+            errors.append(e)
+
+    lib.mg_set_concurrent_factorizations(workers)
+    try:
+        threads = [threading.Thread(target=work, args=(s,), name=f"mg-mlp-{i}") for i, s in enumerate(streams)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for s in streams:
+            caller.wait_stream(s)
+    finally:
+        lib.mg_set_concurrent_factorizations(1)
+    if errors:
+        raise errors[0]
+
+
+_WORKER_STREAMS: dict = {}
+
+
+def _worker_streams(device, n: int) -> list:
+    pool = _WORKER_STREAMS.setdefault(torch.device(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]

@@ -50,6 +50,9 @@ struct Lanes {
   int bulk_cta_cap() const;   // persistent-grid cap for GEMMs on upd / tri (0 = none)
 };
 
+// The bulk GEMMs of `n` concurrent factorisations share the SMs left after the chain reserve.
+void set_lane_share(int n);
+
 // RAII: fork the caller's stream into the lanes (holding the per-device lane mutex), join on
 // destruction.  `ok()` is false if the streams could not be created; the drivers then run serial.
 class LaneScope {

@@ -4,8 +4,11 @@
 //   * the right-looking blocked Cholesky driver whose TRSM and trailing SYRK run on tcgen05.
 #include "mg_linalg.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "mg_gemm.cuh"
 #include "mg_once.cuh"
@@ -534,7 +537,21 @@ struct DeviceLanes {
 
 // Two independent lane sets per device: two host threads can run two factorisations side by side
 // (different layers; each chain is latency-bound and leaves most SMs idle).
-constexpr int kLaneSets = 2;
+constexpr int kLaneSets = 3;
+
+int lane_slot_for(cudaStream_t user) {
+  static std::mutex mu;
+  static std::vector<std::pair<cudaStream_t, int>> seen;
+  static int next = 0;
+  std::lock_guard<std::mutex> g(mu);
+  for (const auto& e : seen)
+    if (e.first == user) return e.second;
+  const int slot = next++ % kLaneSets;
+  if (seen.size() > 64) seen.clear();     // streams come and go: forget, reassign
+  seen.emplace_back(user, slot);
+  return slot;
+}
+
 DeviceLanes& device_lanes(int slot) {
   static DeviceLanes per_dev[64][kLaneSets];
   int dev = 0;
@@ -560,10 +577,20 @@ bool lanes_disabled() {
 }
 }  // namespace
 
+// Number of factorisations the caller runs side by side (mg_set_concurrent_factorizations): the
+// SMs left after the chain reserve are divided between their bulk GEMMs, so that no persistent
+// grid can fill the GPU and starve the OTHER factorisation's latency-bound chain kernels.
+std::atomic<int> g_lane_share{1};
+
 int Lanes::bulk_cta_cap() const {
-  const int cap = device_sm_count() - reserve_sms;
-  return serial ? 0 : (cap < 16 ? 16 : cap);
+  if (serial) return 0;
+  const int share = g_lane_share.load(std::memory_order_relaxed);
+  int cap = (device_sm_count() - reserve_sms) / (share < 1 ? 1 : share);
+  cap &= ~1;                       // CTA pairs
+  return cap < 16 ? 16 : cap;
 }
+
+void set_lane_share(int n) { g_lane_share.store(n < 1 ? 1 : (n > 4 ? 4 : n), std::memory_order_relaxed); }
 
 LaneScope::LaneScope(cudaStream_t user, int64_t n) {
   // measured at n = 11008: Nystrom 12.8 -> 11.7 ms going from 4 to 52 reserved SMs (chain-bound);
@@ -576,14 +603,13 @@ LaneScope::LaneScope(cudaStream_t user, int64_t n) {
   lanes_.user = lanes_.chain = lanes_.chain2 = lanes_.upd = lanes_.tri = lanes_.tri2 = user;
   lanes_.serial = true;
   if (lanes_disabled()) return;
-  DeviceLanes* dp = nullptr;
-  for (int slot = 0; slot < kLaneSets && !dp; ++slot)
-    if (device_lanes(slot).mu.try_lock()) dp = &device_lanes(slot);
-  if (!dp) {
-    dp = &device_lanes(0);
-    dp->mu.lock();
-  }
-  DeviceLanes& d = *dp;
+  // One lane set per CALLER STREAM (assigned round-robin the first time a stream is seen): two host
+  // threads that decompose different layers on different streams then never share internal streams.
+  // (Picking whichever set happened to be unlocked at enqueue time — round 1 — put both threads on
+  // set 0 most of the time: a factorisation is enqueued in 3 ms and runs for 10, so the lock was
+  // usually free, and the second factorisation queued behind the first on the same streams.)
+  DeviceLanes& d = device_lanes(lane_slot_for(user));
+  d.mu.lock();
   lock_ = &d;
   if (!d.tried) {
     d.tried = true;
@@ -751,6 +777,12 @@ int CholStepper::step(int64_t pj) const {
   const int64_t tw = rest < 384 ? rest : 384;
   const int64_t sw = tw;
   const int64_t fr = rest < kNB ? rest : kNB;       // rows of the next block row
+  // Block row pj, columns [c0, c0 + 384): the first 256 received panel pj-1's update from the
+  // chain's own tile update, the last 128 from chain2's row update of panel pj-1 — a cross-lane
+  // dependency.  (Round 1 waited for it only before the tile update below; the solve ran ahead of
+  // it, protected by nothing but the 70 us of potrf128 in between — it broke once two
+  // factorisations shared the GPU.)
+  if (pj >= 1) L.wait(L.chain, L.row_rest[(pj - 1) & 1]);
   MG_TIMED(L.chain, "chol.trsm128_first",
            rc = trsm128(tf, false, nb, a12, ld, sw, 1.f, a12, ld, u12, np, pstride, l21, np, pstride,
                         nullptr, L.chain));

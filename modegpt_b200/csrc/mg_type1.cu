@@ -348,6 +348,11 @@ __global__ void __launch_bounds__(1024, 1) select_k_kernel(const float* __restri
 // =================================================================================================
 extern "C" {
 
+int mg_set_concurrent_factorizations(int n) {
+  mg::set_lane_share(n);
+  return 0;
+}
+
 size_t mg_ridge_scores_ws_bytes(int64_t n) { return carve_scores(nullptr, n).bytes; }
 
 int mg_ridge_scores_f32(const float* C, int64_t n, int64_t ldc, float ridge, float* scores,

@@ -4,6 +4,8 @@ torch is used only for device memory and streams; all arithmetic happens in libm
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ._lib import check, lib
@@ -121,8 +123,14 @@ class NotPositiveDefinite(RuntimeError):
         self.pivot = pivot
 
 
+_POISON_WS = os.environ.get("MG_POISON_WS", "0") == "1"
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if _POISON_WS:      # tests: every byte 0xFF (NaN as bf16 / fp32 / fp64) — a kernel that reads
+        ws.fill_(0xFF)  # workspace it did not write shows up as NaNs instead of passing by luck
+    return ws
 
 
 def _f32_square(C: torch.Tensor, name: str) -> tuple[int, int]:

@@ -218,6 +218,70 @@ def test_type1_graded_statistic_with_massive_channels(ops):
     _bf16_close(ops.nystrom_down(c, idx, wd.to(DEV)), want["down"], frac=0.94)
 
 
+def test_type1_concurrent_factorizations_are_timing_independent(ops):
+    """Two host threads decomposing on two streams (two internal lane sets, bulk GEMMs sharing the
+    SMs) while a third stream hammers the GPU: every result must be bit-identical to the quiet
+    single-stream one.  Round 2's stress run (tools/gpu_stress_type1.py) found a cross-lane
+    dependency of the split-chain Cholesky step that only timing had protected; this is its
+    regression test at a size that still has 24 panels / 6 outer blocks."""
+    import threading
+
+    from modegpt_b200._lib import lib
+
+    n, d, k = 3072, 256, 2304
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = (torch.randn(4 * n, n, device=DEV, generator=g)
+         * torch.exp(0.7 * torch.randn(n, device=DEV, generator=g))).bfloat16()
+    c = torch.zeros(n, n, device=DEV)
+    ops.syrk_(c, x)
+    ops.finalize_sym_(c, 1.0 / (4 * n))
+    wd = (torch.randn(d, n, device=DEV, generator=g) * 0.05).bfloat16()
+    torch.cuda.synchronize()
+
+    def once():
+        s = ops.ridge_scores(c, 1e-4)
+        idx = ops.select_k(s, k)
+        return s, idx, ops.nystrom_down(c, idx, wd)
+
+    ref = once()
+    torch.cuda.synchronize()
+    stop, errors, results = [False], [], {0: [], 1: []}
+
+    def noise():
+        st = torch.cuda.Stream()
+        a = torch.randn(6144, 6144, device=DEV, dtype=torch.bfloat16)
+        with torch.cuda.stream(st):
+            while not stop[0]:
+                a @ a
+                st.synchronize()
+
+    def worker(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(6):
+                    results[i].append(once())
+            st.synchronize()
+        except BaseException as e:
+            errors.append(e)
+
+    lib.mg_set_concurrent_factorizations(2)
+    try:
+        threads = [threading.Thread(target=noise)] + [threading.Thread(target=worker, args=(i,)) for i in (0, 1)]
+        for t in threads:
+            t.start()
+        for t in threads[1:]:
+            t.join()
+        stop[0] = True
+        threads[0].join()
+    finally:
+        lib.mg_set_concurrent_factorizations(1)
+    assert not errors, errors
+    for i in (0, 1):
+        for s, idx, down in results[i]:
+            assert torch.equal(s, ref[0]) and torch.equal(idx, ref[1]) and torch.equal(down, ref[2])
+
+
 def test_select_k_edge_cases(ops):
     s = torch.tensor([3.0, 1.0, 2.0, 1.0, 5.0, 1.0, -2.0, 0.0], device=DEV)
     assert ops.select_k(s, 3).tolist() == [1, 6, 7]                 # ties resolve to the lower index

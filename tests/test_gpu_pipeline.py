@@ -233,6 +233,29 @@ def test_full_rank_roundtrip_preserves_the_model(tmp_path, preset, monkeypatch):
     assert err < 5e-2, err
 
 
+def test_type1_workers_do_not_change_results(golden, tmp_path):
+    """compress_nystrom with two worker threads (two streams, two lane sets, the bulk GEMMs' SM
+    share halved by mg_set_concurrent_factorizations) produces the same layer tensors as the
+    single-threaded loop."""
+    from modegpt_b200.compression.compress_mlp import compress_nystrom
+
+    g = golden("pipeline_llama_gqa")
+    L = int(g["cfg"][2])
+    f32 = lambda k: torch.tensor(g[k], device=DEV, dtype=torch.float32)
+    keep = [float(x) for x in g["keep"]]
+    out = {}
+    for workers in (1, 2):
+        adapter = make_adapter(g, tmp_path, keep_layers_in_memory=True, mlp_workers=workers)
+        compress_nystrom(adapter, [f32(f"cov_mlp{l}") for l in range(L)], keep, list(range(L)))
+        torch.cuda.synchronize()
+        out[workers] = dict(adapter._layer_store)
+    assert set(out[1]) == set(out[2]) == {(l, "mlp") for l in range(L)}
+    for key in out[1]:
+        for name in ("up", "gate"):
+            assert torch.equal(out[1][key][name], out[2][key][name])
+        assert rel(out[2][key]["down"].float().cpu().numpy(), out[1][key]["down"].float().cpu().numpy()) < 2e-3
+
+
 def test_type3_grouped_layers_match_one_at_a_time(golden, tmp_path):
     """compress_vo in groups (mg_vo_prepare back to back, mg_vo_finish on one stream per layer) is
     the same computation as one mg_vo_compress per layer: bit-identical tensors."""
