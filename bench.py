@@ -276,6 +276,7 @@ def run_gpu_arm(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tf_peak, hbm_peak, peak_src = peaks()
+    sys.setswitchinterval(5e-4)     # as run_modegpt.main does (launch threads vs writer threads)
 
     model = build_synthetic_model(PRESET, device=str(dev), seed=0)
     adapter = ModelAdapter.from_model(model, tokenizer=None)

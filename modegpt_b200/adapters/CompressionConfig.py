@@ -41,7 +41,7 @@ class CompressionConfig:
     seed: int = 1234               # calibration token seed (reference seeds are 1234)
     keep_layers_in_memory: bool = False   # hand layers to convert_model without the disk round trip
     vo_group: int = 0                     # type-III layers whose eigensolves run side by side (0 = auto, 1 = one at a time)
-    mlp_workers: int = 1                  # type-I layers decomposed side by side (threads + streams; SMs shared)
+    mlp_workers: int = 2                  # type-I layers decomposed side by side (threads + streams; bulk GEMMs share the SMs)
     sync_save: bool = False               # blocking torch.save per layer, as the reference does
     stream_layers: bool = False           # layer-streamed calibration: one layer's statistics at a time
     eager_forward: bool = False           # keep HF's eager elementwise kernels in the calibration forward

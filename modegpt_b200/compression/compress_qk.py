@@ -28,8 +28,13 @@ SQRT_M_DEFAULT_RIDGE = 1e-4  # src/compression_utils.py:17
 
 @torch.no_grad()
 def compress_qk(adapter: ModelAdapter, cov, keep_ratios, rank=None, slice_dims=True,
-                target_layers: list[int] | None = None):
-    """Returns the rotary masks ([KV, r] int64, one per target layer, in layer order)."""
+                target_layers: list[int] | None = None, local_masks: dict | None = None):
+    """Returns the rotary masks ([KV, r] int64, one per target layer, in layer order).
+
+    `local_masks` (additive): a dict that receives this rank's {layer: mask} INSTEAD of the
+    cross-rank gather — the layer-streamed flow calls this once per layer and would otherwise put a
+    collective (a synchronisation of all ranks on the owner's decomposition) into every layer; it
+    gathers once at the end with `gather_rotary_masks`."""
     if target_layers is None:
         target_layers = list(range(adapter.n_layers))
     cov_q_list, cov_k_list = cov
@@ -43,11 +48,23 @@ def compress_qk(adapter: ModelAdapter, cov, keep_ratios, rank=None, slice_dims=T
         logger.info(f"[QK] Layer {i}: compressed to rank {rank_i} per head (CR score)")
     if not slice_dims:
         return None
+    if local_masks is not None:
+        local_masks.update(local)
+        return None
     if D.is_distributed():
         device = next(adapter.model.parameters()).device
         merged = D.gather_masks(local, adapter.n_layers, adapter.n_kv_heads, hd, device)
         return [merged[i] for i in target_layers if merged[i] is not None]
     return [local[i] for i in target_layers if i in local]
+
+
+def gather_rotary_masks(adapter: ModelAdapter, local_masks: dict, target_layers: list[int]) -> list:
+    """Every rank's {layer: mask} -> the full list in layer order on every rank (one collective)."""
+    if D.is_distributed():
+        device = next(adapter.model.parameters()).device
+        merged = D.gather_masks(local_masks, adapter.n_layers, adapter.n_kv_heads, adapter.head_dim, device)
+        return [merged[i] for i in target_layers if merged[i] is not None]
+    return [local_masks[i] for i in target_layers if i in local_masks]
 
 
 @torch.no_grad()

@@ -67,6 +67,11 @@ def _run_stages_serial(stages: dict, timings: dict, device: str) -> dict:
 def main(trial=None, config: CompressionConfig | None = None):
     _setup_logging()
     gc.collect()
+    import sys
+
+    # kernel-launching threads (type-I workers) share the interpreter with the layer-writer
+    # threads; a 5 ms switch interval lets a writer's pickling delay a launch sequence by that much
+    sys.setswitchinterval(5e-4)
     config = config or CompressionConfig.from_args()
     device = _init_distributed(config)
     is_root = D.rank() == 0
@@ -112,6 +117,7 @@ def main(trial=None, config: CompressionConfig | None = None):
                                         smoothing=config.sparsity_smoothing,
                                         max_sparsity=config.max_sparsity, adapter=adapter)
         stats = iter_layer_statistics(adapter, dataset=config.dataset)
+        streamed_masks: dict = {}       # gathered once after the loop: no collective per layer
         while True:
             item = timed("calibration_s", lambda: next(stats, None))
             if item is None:
@@ -122,13 +128,16 @@ def main(trial=None, config: CompressionConfig | None = None):
                 timed("mlp_s", lambda: compress_nystrom(adapter=adapter, cov=one(c_mlp), keep_ratios=keep,
                                                         target_layers=[l]))
             if "qk" in config.order:
-                masks = timed("qk_s", lambda: compress_qk(adapter=adapter, cov=(one(c_q), one(c_k)),
-                                                         keep_ratios=keep, target_layers=[l]))
-                rotary_masks.extend(masks or [])
+                timed("qk_s", lambda: compress_qk(adapter=adapter, cov=(one(c_q), one(c_k)), keep_ratios=keep,
+                                                  target_layers=[l], local_masks=streamed_masks))
             if "vo" in config.order:
                 timed("vo_s", lambda: compress_vo(adapter=adapter, cov=one(c_x), keep_ratios=keep,
                                                   target_layers=[l]))
             del item, c_mlp, c_q, c_k, c_x
+        if "qk" in config.order:
+            from .compression.compress_qk import gather_rotary_masks
+
+            rotary_masks.extend(gather_rotary_masks(adapter, streamed_masks, list(range(n_layers))))
         torch.cuda.empty_cache()
 
     for start in (() if config.stream_layers else range(0, n_layers, LAYERS_PER_STEP)):

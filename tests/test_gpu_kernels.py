@@ -220,8 +220,7 @@ def test_type1_graded_statistic_with_massive_channels(ops):
 
 def test_type1_concurrent_factorizations_are_timing_independent(ops):
     """Two host threads decomposing on two streams (two internal lane sets, bulk GEMMs sharing the
-    SMs) while a third stream hammers the GPU: every result must be bit-identical to the quiet
-    single-stream one.  Round 2's stress run (tools/gpu_stress_type1.py) found a cross-lane
+    SMs) while a third stream hammers the GPU: every result must match the quiet single-stream one.  Round 2's stress run (tools/gpu_stress_type1.py) found a cross-lane
     dependency of the split-chain Cholesky step that only timing had protected; this is its
     regression test at a size that still has 24 panels / 6 outer blocks."""
     import threading
@@ -277,9 +276,16 @@ def test_type1_concurrent_factorizations_are_timing_independent(ops):
     finally:
         lib.mg_set_concurrent_factorizations(1)
     assert not errors, errors
+    # same block operations in the same order; only the order of split-K partial sums in L2 is
+    # free (last-bit differences in the scores), so: scores to 1e-5, selection identical, W_down
+    # identical up to isolated bf16 roundings.  The race this guards against produced different
+    # SELECTIONS and O(0.2) errors in W_down.
     for i in (0, 1):
         for s, idx, down in results[i]:
-            assert torch.equal(s, ref[0]) and torch.equal(idx, ref[1]) and torch.equal(down, ref[2])
+            assert rel(s.cpu().numpy(), ref[0].cpu().numpy()) < 1e-5
+            assert torch.equal(idx, ref[1])
+            assert (down == ref[2]).float().mean() > 0.99
+            assert rel(down.float().cpu().numpy(), ref[2].float().cpu().numpy()) < 1e-3
 
 
 def test_select_k_edge_cases(ops):

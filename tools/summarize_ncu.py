@@ -21,7 +21,10 @@ OWN = ["bi_cosine_kernel", "finalize_sym_kernel", "scale_kernel", "split_planes_
        "trsm128_kernel", "select_k_kernel", "gather_rows_kernel", "gather_sym_kernel",
        "gather_cols_planes_kernel", "copy_ridge_kernel", "identity_kernel", "transpose_to_bf16_kernel",
        "transpose_bf16_kernel", "qk_select_kernel", "vo_factor_kernel", "vo_apply_v_kernel",
-       "vo_apply_o_kernel", "diag_block_kernel", "ydiag_kernel"]
+       "vo_apply_o_kernel", "diag_block_kernel", "ydiag_kernel", "rmsnorm_kernel", "swiglu_kernel",
+       "rope_kernel", "rope_masked_kernel", "rmsnorm_masked_kernel", "ce_rows_kernel", "pack_upper_kernel",
+       "gram64_kernel", "f32_to_f64_kernel", "copy_upper_ridge_kernel", "mark_kept_kernel",
+       "sub_jitter_rows_kernel", "add_kept_transpose_kernel"]
 
 
 def short_name(name: str) -> str:
