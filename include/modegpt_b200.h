@@ -109,11 +109,27 @@ int mg_gather_rows_bf16(const void* W, int64_t ldw, const int64_t* idx, int64_t 
 
 /* Wd_out[d, k] (bf16) = ((C[idx,idx] + jitter I)^-1 (C[idx, :] Wd^T))^T.
  * C: fp32 [n,n] FULL symmetric (both triangles valid); Wd: bf16 [d, n].
+ * Solved in correction form (only the dropped channels' contribution passes through the fp32
+ * factor).  *min_rel_pivot (device, may be NULL) receives min_i U_ii^2 / A_ii of the Cholesky factor
+ * of A = C[idx,idx] + jitter I — a conditioning indicator of the EQUILIBRATED system: the fp32
+ * solve is accurate to about 1e-7 / min_rel_pivot.
  * Replaces src/compression/compress_mlp.py:52-57 (+ the transpose at :97). */
 size_t mg_nystrom_down_ws_bytes(int64_t n, int64_t k, int64_t d);
 int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* idx, int64_t k,
                         const void* Wd, int64_t d, int64_t ldwd, float jitter, void* Wd_out,
-                        int64_t ld_out, void* ws, size_t ws_bytes, int* info, void* stream);
+                        int64_t ld_out, void* ws, size_t ws_bytes, int* info, float* min_rel_pivot,
+                        void* stream);
+
+/* One sweep of iterative refinement of the solution mg_nystrom_down_f32 left in `ws` (same C, idx,
+ * k, d, jitter, ws; call right after it on the same stream, after checking *info == 0): the
+ * residual C[idx,:] Wd^T - (C[idx,idx] + jitter I) X is formed in FP64 (CUDA cores, 2 k n d flop),
+ * the correction is solved with the fp32 factor, Wd_out is rewritten.  Each sweep multiplies the
+ * error by about 1e-7 / min_rel_pivot; the reference solves in fp64 (compress_mlp.py:56-57), and
+ * this is how an ill-conditioned C_kk (ReLU-sparse OPT activations, heavy compression) reaches
+ * the same bf16 result. */
+int mg_nystrom_refine_f32(const float* C, int64_t n, int64_t ldc, const int64_t* idx, int64_t k,
+                          int64_t d, float jitter, void* Wd_out, int64_t ld_out, void* ws,
+                          size_t ws_bytes, void* stream);
 
 /* ---- type-II: CR Q/K ------------------------------------------------------------------------- */
 

@@ -36,7 +36,8 @@ SIGNATURES: dict[str, tuple] = {
     "mg_gather_rows_bf16": (i32, [vp, i64, vp, i64, i64, vp, i64, vp]),
     "mg_nystrom_down_ws_bytes": (C.c_size_t, [i64, i64, i64]),
     "mg_nystrom_down_f32": (i32, [vp, i64, i64, vp, i64, vp, i64, i64, f32, vp, i64, vp,
-                                  C.c_size_t, vp, vp]),
+                                  C.c_size_t, vp, vp, vp]),
+    "mg_nystrom_refine_f32": (i32, [vp, i64, i64, vp, i64, i64, f32, vp, i64, vp, C.c_size_t, vp]),
     "mg_qk_select_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp]),
     "mg_gather_head_rows_bf16": (i32, [vp, i64, vp, i32, i32, i64, i64, i64, vp, i64, vp]),
     "mg_vo_ws_bytes": (C.c_size_t, [i64, i32, i32, i32]),

@@ -45,7 +45,11 @@ def compress_weights(comps: MLPComponents, C: Tensor, keep_ratio: float, layer_i
     gate = None
     if comps.gate_proj is not None:
         gate = ops.gather_rows(comps.gate_proj.weight.detach(), idx)
-    down = ops.nystrom_down(C, idx, comps.down_proj.weight.detach().contiguous(), NYSTROM_JITTER)
+    stats: dict = {}
+    down = ops.nystrom_down(C, idx, comps.down_proj.weight.detach().contiguous(), NYSTROM_JITTER, stats=stats)
+    if stats.get("refine_sweeps"):
+        logger.info(f"[MLP] Layer {layer_idx}: C_kk min relative pivot {stats['min_rel_pivot']:.1e} -> "
+                    f"{stats['refine_sweeps']} fp64-residual refinement sweep(s)")
     return up.T, down.T, (gate.T if gate is not None else None), rank, idx
 
 

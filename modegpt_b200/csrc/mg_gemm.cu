@@ -787,21 +787,6 @@ int gemm_tn_launch(const GemmArgs& a, cudaStream_t stream) {
 
   int cta_cap = device_sm_count();
   if (a.max_ctas >= 2 && a.max_ctas < cta_cap) cta_cap = a.max_ctas;
-  // Bulk GEMMs of the blocked drivers (the ones that pass max_ctas): instead of a persistent grid
-  // capped at max_ctas CTAs — whose CTAs hold their SMs for the whole GEMM — launch one CTA per
-  // `tiles_per_cta` units of work.  CTAs then retire every few tens of microseconds, so the
-  // latency-critical panel kernels of this and of concurrent factorisations find a free SM at once
-  // and concurrent bulk GEMMs share the SMs at tile granularity.  (MG_BULK_TILES_PER_CTA, 0 = off)
-  static const int bulk_tpc = [] {
-    const char* e = std::getenv("MG_BULK_TILES_PER_CTA");
-    return e ? std::atoi(e) : 0;
-  }();
-  if (a.max_ctas >= 2 && bulk_tpc > 0) {
-    // work units are tiles (x split-K) of one CTA, or of one CTA PAIR on the cluster path
-    const int want = (kp.total_work + bulk_tpc - 1) / bulk_tpc * (pair ? 2 : 1);
-    if (want > cta_cap) cta_cap = want;             // may exceed the SM count: CTAs queue in hardware
-  }
-
   CUtensorMap tmA, tmB;
   int rc = make_plane_map(&tmA, a.A, a.M, a.K, a.lda, a.a_planes, a.a_plane_stride);
   if (rc) return rc;

@@ -75,6 +75,8 @@ struct NystromWs {
   bf16* zb_planes;  // [3][4*128 x dp]    forward substitution: Z planes of one outer block
   bf16* xb_planes;  // [2][3][4*128 x dp] back-substitution: X planes of an outer block (double-buffered)
   uint8_t* kept;    // [n]                1 where the channel is in idx
+  int32_t* pos;     // [n]                position of channel l inside idx, -1 if dropped
+  float* xacc;      // [k x dp]           the full solution W_down'^T (fp32), refined in place
   mg::CholWorkspace chol;
   size_t bytes;
 };
@@ -92,6 +94,8 @@ NystromWs carve_nystrom(void* p, int64_t n, int64_t k, int64_t d) {
   w.zb_planes = c.take<bf16>(kPlanes * 4 * kNB * dp);
   w.xb_planes = c.take<bf16>(2 * kPlanes * 4 * kNB * dp);
   w.kept = c.take<uint8_t>(n);
+  w.pos = c.take<int32_t>(n);
+  w.xacc = c.take<float>(k * dp);
   w.chol.u_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.l_planes = c.take<bf16>(kPlanes * kp * kp);
   w.chol.t_fwd = c.take<float>(panels * mg::kTBlock);
@@ -248,6 +252,119 @@ __global__ void __launch_bounds__(256) add_kept_transpose_kernel(const float* __
   }
 }
 
+// kept[l] = 1 and pos[l] = i for l = idx_i (pos = -1 elsewhere: cleared by the caller)
+__global__ void mark_kept_pos_kernel(const int64_t* __restrict__ idx, int64_t k, uint8_t* __restrict__ kept,
+                                     int32_t* __restrict__ pos) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < k) {
+    kept[idx[i]] = 1;
+    pos[idx[i]] = static_cast<int32_t>(i);
+  }
+}
+
+__global__ void set_float_kernel(float* p, float v) { *p = v; }
+
+// *out = min(*out, min_i U_ii^2 / (C[idx_i, idx_i] + jitter)); positive floats order like their bits
+__global__ void __launch_bounds__(256) min_rel_pivot_kernel(const float* __restrict__ C, int64_t ldc,
+                                                            const int64_t* __restrict__ idx, int64_t k,
+                                                            const float* __restrict__ U, int64_t ldu,
+                                                            float jitter, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float r = 3.0e38f;
+  if (i < k) {
+    const float u = U[i * ldu + i];
+    const float a = C[idx[i] * ldc + idx[i]] + jitter;
+    r = a > 0.f ? u * u / a : 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = fminf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(reinterpret_cast<int*>(out), __float_as_int(fmaxf(r, 0.f)));
+}
+
+// xacc[i, c] = X[i, c] + Wd^T[idx_i, c]   (the full solution W_down'^T = W_down[:, idx]^T + correction)
+__global__ void __launch_bounds__(256) add_kept_rows_kernel(const float* __restrict__ x, int64_t ldx,
+                                                            const bf16* __restrict__ wdt, int64_t ldw,
+                                                            const int64_t* __restrict__ idx, int64_t d,
+                                                            float* __restrict__ xacc, int accumulate) {
+  const int64_t i = blockIdx.x;
+  const bf16* src = wdt + idx[i] * ldw;
+  for (int64_t c = threadIdx.x; c < d; c += blockDim.x) {
+    const float base = accumulate ? xacc[i * ldx + c] : __bfloat162float(src[c]);
+    xacc[i * ldx + c] = base + x[i * ldx + c];
+  }
+}
+
+// FP64 residual of the Nystrom system for the current solution X (fp32, xacc [k x ldx]):
+//     R = C[idx, :] W_d^T - (C_kk + jitter I) X  =  C[idx, :] E - jitter X,
+//     E[l, c] = W_d^T[l, c] - (l kept ? X[pos_l, c] : 0)
+// — one GEMM over ALL n channels whose kept rows carry the (small) difference W_d^T - X formed
+// exactly in fp64, so the cancellation that defeats an fp32 right-hand side never happens.  C is
+// fp32, W_d bf16, X fp32: every product is exact in fp64 and the accumulation is fp64 (CUDA cores,
+// 8 x 8 register tiles; 2 k n d flop).  The result is rounded once, to the fp32 right-hand side of
+// the correction solve.
+constexpr int kResKC = 16;
+__global__ void __launch_bounds__(256)
+    nystrom_resid64_kernel(const float* __restrict__ C, int64_t ldc, int64_t n,
+                           const int64_t* __restrict__ idx, int64_t k, const bf16* __restrict__ wdt,
+                           int64_t ldw, const int32_t* __restrict__ pos, const float* __restrict__ xacc,
+                           int64_t ldx, int64_t d, float jitter, float* __restrict__ rhs) {
+  __shared__ double As[kResKC][128 + 1];
+  __shared__ double Es[kResKC][128 + 1];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 128, c0 = static_cast<int64_t>(blockIdx.y) * 128;
+  double acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+  for (int64_t l0 = 0; l0 < n; l0 += kResKC) {
+    __syncthreads();
+    // As[ll][ii] = C[idx[i0 + ii], l0 + ll]: consecutive threads walk l (contiguous in C's row)
+    for (int e = t; e < 128 * kResKC; e += 256) {
+      const int ll = e & (kResKC - 1), ii = e / kResKC;
+      const int64_t i = i0 + ii, l = l0 + ll;
+      As[ll][ii] = (i < k && l < n) ? static_cast<double>(C[idx[i] * ldc + l]) : 0.0;
+    }
+    // Es[ll][cc] = E[l0 + ll, c0 + cc]: consecutive threads walk c (contiguous in wdt and in xacc)
+    for (int e = t; e < 128 * kResKC; e += 256) {
+      const int cc = e & 127, ll = e >> 7;
+      const int64_t c = c0 + cc, l = l0 + ll;
+      double v = 0.0;
+      if (c < d && l < n) {
+        v = static_cast<double>(__bfloat162float(wdt[l * ldw + c]));
+        const int32_t pl = pos[l];
+        if (pl >= 0) v -= static_cast<double>(xacc[static_cast<int64_t>(pl) * ldx + c]);
+      }
+      Es[ll][cc] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int ll = 0; ll < kResKC; ++ll) {
+      double av[8], ev[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) av[a] = As[ll][ty + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) ev[b] = Es[ll][tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = fma(av[a], ev[b], acc[a][b]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int64_t i = i0 + ty + 16 * a;
+    if (i >= k) continue;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int64_t c = c0 + tx + 16 * b;
+      if (c < d)
+        rhs[i * ldx + c] = static_cast<float>(acc[a][b] - static_cast<double>(jitter) *
+                                                               static_cast<double>(xacc[i * ldx + c]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- radix select
 __device__ __forceinline__ uint32_t order_key(float x, int largest) {
   uint32_t u = __float_as_uint(x);
@@ -339,6 +456,202 @@ __global__ void __launch_bounds__(1024, 1) select_k_kernel(const float* __restri
     }
     __syncthreads();
   }
+}
+
+// Forward + backward substitution of w.rhs [k x dp] with the factor in w.chol / w.ckk, in place
+// (rhs -> Z -> X).  With `chol` the factorisation steps ride along (first solve: step pi needs
+// block row pi of U and nothing later); without it the factor is complete (refinement solves).
+int nystrom_solves(const NystromWs& w, const mg::Lanes& L, int64_t k, int64_t d, const mg::CholStepper* chol) {
+  const int64_t kp = w.chol.n_pad, dp = mg::round_up(d, 64);
+  const int64_t pstride = kp * kp;
+  const int64_t panels = (k + kNB - 1) / kNB;
+  int rc;
+  // ---- forward solve  U^T Z = rhs  (right-looking, in place) rides one panel behind the
+  //      factorisation on the tri lane: step pi needs block row pi of U and nothing later
+  //      Two-level blocking like the factorisation: inside an outer block of kFwdOuter panels a
+  //      panel only updates the block's remaining rows (K = 128); the rows below the block get one
+  //      update per block with K = kFwdOuter * 128 from the block's stacked Z planes — a quarter
+  //      of the read-modify-write passes over rhs.
+  constexpr int64_t kFwdOuter = 4;
+  const int64_t zb_stride = kFwdOuter * kNB * dp;      // plane stride of the stacked Z block
+  for (int64_t pi = 0; pi < panels; ++pi) {
+    if (chol) {
+      if ((rc = chol->step(pi))) return rc;
+      L.wait(L.tri, L.trsm);
+    }
+    const int64_t i0 = pi * kNB;
+    const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+    float* bi = w.rhs + i0 * dp;
+    const int64_t rest = k - i0 - nb;
+    const int64_t q = pi % kFwdOuter, o0 = (pi - q) * kNB;
+    const int64_t o_end = (o0 + kFwdOuter * kNB < k) ? o0 + kFwdOuter * kNB : k;
+    bf16* zq = w.zb_planes + q * kNB * dp;              // this panel's rows inside the Z block
+    // Z_i = U_ii^-T B_i (+ planes of Z_i for the updates below)
+    MG_TIMED(L.tri, "nystrom.fwd_trsm",
+             rc = mg::trsm128(w.chol.t_fwd + pi * mg::kTBlock, false, nb, bi, dp, d, 1.f, bi, dp,
+                              rest > 0 ? zq : nullptr, dp, zb_stride, nullptr, 0, 0, nullptr, L.tri));
+    if (rc) return rc;
+    if (rest <= 0) break;
+    mg::GemmArgs t{};
+    t.lda = kp;
+    t.a_plane_stride = pstride;
+    t.a_planes = kPlanes;
+    t.ldb = dp;
+    t.b_plane_stride = zb_stride;
+    t.b_planes = kPlanes;
+    pairs6(t);
+    t.N = d;
+    t.ldd = dp;
+    t.alpha = -1.f;
+    t.tiles = mg::TILES_FULL;
+    t.epi = mg::EPI_ADD;
+    t.ksplit = 1;
+    t.max_ctas = L.bulk_cta_cap();
+    const int64_t in_block = o_end - (i0 + nb);
+    if (in_block > 0) {            // B[block rows below] -= U[ib, those rows]^T Z_i
+      t.A = w.chol.u_planes + i0 * kp + (i0 + nb);
+      t.B = zq;
+      t.M = in_block;
+      t.K = nb;
+      t.D = w.rhs + (i0 + nb) * dp;
+      MG_TIMED(L.tri, "nystrom.fwd_update_in_block", rc = mg::gemm_tn_launch(t, L.tri));
+    } else {                       // B[rows below the block] -= U[block rows, those rows]^T Z_block
+      t.A = w.chol.u_planes + o0 * kp + o_end;
+      t.B = w.zb_planes;
+      t.M = rest;
+      t.K = o_end - o0;
+      t.D = w.rhs + o_end * dp;
+      MG_TIMED(L.tri, "nystrom.fwd_update", rc = mg::gemm_tn_launch(t, L.tri));
+    }
+    if (rc) return rc;
+  }
+  // ---- backward solve  U X = Z  on the chain lane, once the forward pass and every trailing
+  //      update have landed
+  L.record(L.misc[0], L.tri);
+  L.wait(L.chain, L.misc[0]);
+  L.record(L.misc[1], L.upd);
+  L.wait(L.chain, L.misc[1]);
+  L.record(L.row_rest[0], L.chain2);
+  L.wait(L.chain, L.row_rest[0]);
+  //      Two-level blocking + look-ahead, mirrored from the factorisation (panels run from the
+  //      last to the first): inside an outer block a panel only updates the block's rows above it
+  //      (K = 128, chain lane); when the block's first panel is solved, the rows above the block
+  //      get the whole block at once (K = 512) — the next block's last block row on the chain
+  //      lane, its other rows and everything above on the upd lane.
+  if (L.serial) {
+    for (int64_t pi = panels - 1; pi >= 0; --pi) {
+      const int64_t i0 = pi * kNB;
+      const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+      float* zi = w.rhs + i0 * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_trsm",
+               rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
+                                i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
+                                L.chain));
+      if (rc) return rc;
+      if (i0 == 0) break;
+      mg::GemmArgs t{};
+      t.A = w.chol.l_planes + i0 * kp;   // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
+      t.lda = kp;
+      t.a_plane_stride = pstride;
+      t.a_planes = kPlanes;
+      t.B = w.z_planes;
+      t.ldb = dp;
+      t.b_plane_stride = kNB * dp;
+      t.b_planes = kPlanes;
+      pairs6(t);
+      t.M = i0;
+      t.N = d;
+      t.K = nb;
+      t.D = w.rhs;
+      t.ldd = dp;
+      t.alpha = -1.f;
+      t.tiles = mg::TILES_FULL;
+      t.epi = mg::EPI_ADD;
+      t.ksplit = 1;
+      MG_TIMED(L.chain, "nystrom.bwd_update", rc = mg::gemm_tn_launch(t, L.chain));
+      if (rc) return rc;
+    }
+  } else {
+    const int64_t nblocks = (panels + kFwdOuter - 1) / kFwdOuter;
+    for (int64_t pi = panels - 1; pi >= 0; --pi) {
+      const int64_t i0 = pi * kNB;
+      const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
+      const int64_t ob = pi / kFwdOuter, o0 = ob * kFwdOuter * kNB;
+      const int64_t o_end = (o0 + kFwdOuter * kNB < k) ? o0 + kFwdOuter * kNB : k;
+      // X planes of the block, stacked by row (double-buffered by block parity: the upd lane may
+      // still read block ob while the chain lane fills block ob-1)
+      bf16* xb = w.xb_planes + (ob & 1) * kPlanes * zb_stride;
+      bf16* xq = xb + (i0 - o0) * dp;
+      float* zi = w.rhs + i0 * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_trsm",
+               rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
+                                i0 > 0 ? xq : nullptr, dp, zb_stride, nullptr, 0, 0, nullptr, L.chain));
+      if (rc) return rc;
+      if (i0 == 0) break;
+      mg::GemmArgs t{};
+      t.lda = kp;
+      t.a_plane_stride = pstride;
+      t.a_planes = kPlanes;
+      t.ldb = dp;
+      t.b_plane_stride = zb_stride;
+      t.b_planes = kPlanes;
+      pairs6(t);
+      t.N = d;
+      t.ldd = dp;
+      t.alpha = -1.f;
+      t.tiles = mg::TILES_FULL;
+      t.epi = mg::EPI_ADD;
+      t.ksplit = 1;
+      const int64_t above = i0 - o0;                  // rows of this block above panel pi
+      if (above > 0) {
+        // (ordered adds) the block below updated these rows from the upd lane
+        if (i0 + nb >= o_end && ob + 1 < nblocks) L.wait(L.chain, L.next_done[(ob + 1) & 1]);
+        t.A = w.chol.l_planes + i0 * kp + o0;         // A[k, m] = L[i0 + k, o0 + m] = U[o0 + m, i0 + k]
+        t.B = xq;
+        t.M = above;
+        t.K = nb;
+        t.D = w.rhs + o0 * dp;
+        MG_TIMED(L.chain, "nystrom.bwd_update_in_block", rc = mg::gemm_tn_launch(t, L.chain));
+        if (rc) return rc;
+        continue;
+      }
+      // pi is the block's first panel: rows [0, o0) get the whole block (K = o_end - o0)
+      t.K = o_end - o0;
+      t.B = xb;
+      const int64_t first = kNB;                      // o0 is a multiple of 4 * 128
+      const int64_t next_rows = kFwdOuter * kNB;      // rows of the block above (all of them exist)
+      L.record(L.trsm, L.chain);
+      L.wait(L.upd, L.trsm);
+      {
+        mg::GemmArgs r = t;                           // block above, except its last block row
+        r.A = w.chol.l_planes + o0 * kp + (o0 - next_rows);
+        r.M = next_rows - first;
+        r.D = w.rhs + (o0 - next_rows) * dp;
+        r.max_ctas = L.bulk_cta_cap();
+        MG_TIMED(L.upd, "nystrom.bwd_update_next", rc = mg::gemm_tn_launch(r, L.upd));
+        if (rc) return rc;
+        L.record(L.next_done[ob & 1], L.upd);
+      }
+      if (o0 - next_rows > 0) {                       // everything above that block
+        mg::GemmArgs r = t;
+        r.A = w.chol.l_planes + o0 * kp;
+        r.M = o0 - next_rows;
+        r.D = w.rhs;
+        r.max_ctas = L.bulk_cta_cap();
+        MG_TIMED(L.upd, "nystrom.bwd_update", rc = mg::gemm_tn_launch(r, L.upd));
+        if (rc) return rc;
+      }
+      L.record(L.upd_done[ob & 1], L.upd);
+      // chain: the last block row of the block above (the next panel to be solved)
+      if (ob + 1 < nblocks) L.wait(L.chain, L.upd_done[(ob + 1) & 1]);
+      t.A = w.chol.l_planes + o0 * kp + (o0 - first);
+      t.M = first;
+      t.D = w.rhs + (o0 - first) * dp;
+      MG_TIMED(L.chain, "nystrom.bwd_update_first", rc = mg::gemm_tn_launch(t, L.chain));
+      if (rc) return rc;
+    }
+  }
+  return 0;
 }
 
 }  // namespace
@@ -513,7 +826,8 @@ size_t mg_nystrom_down_ws_bytes(int64_t n, int64_t k, int64_t d) {
 
 int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* idx, int64_t k,
                         const void* Wd, int64_t d, int64_t ldwd, float jitter, void* Wd_out,
-                        int64_t ld_out, void* ws, size_t ws_bytes, int* info, void* stream) {
+                        int64_t ld_out, void* ws, size_t ws_bytes, int* info, float* min_rel_pivot,
+                        void* stream) {
   if (!C || !idx || !Wd || !Wd_out || !ws || !info) return -1;
   if (n <= 0 || k <= 0 || k > n || d <= 0) return -2;
   if (ldc < n || ldwd < n || ld_out < k) return -7;
@@ -535,7 +849,8 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
   // tri lane: operands of the cross term  rhs[k, d] = C[idx, dropped] W_down[:, dropped]^T
   // — independent of the factorisation of C_kk, which starts at once on the chain lane
   cudaMemsetAsync(w.kept, 0, static_cast<size_t>(n), L.tri);
-  mark_kept_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, L.tri>>>(idx, k, w.kept);
+  cudaMemsetAsync(w.pos, 0xFF, sizeof(int32_t) * static_cast<size_t>(n), L.tri);     // -1
+  mark_kept_pos_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, L.tri>>>(idx, k, w.kept, w.pos);
   if ((rc = cuda_rc())) return rc;
   gather_cols_planes_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256 < 16 ? (k + 255) / 256 : 16),
                                    static_cast<unsigned>(n)),
@@ -580,202 +895,54 @@ int mg_nystrom_down_f32(const float* C, int64_t n, int64_t ldc, const int64_t* i
                       256, 0, L.chain>>>(C, ldc, idx, k, w.ckk, kp, jitter);
   if ((rc = cuda_rc())) return rc;
 
-  const int64_t pstride = kp * kp;
-  const int64_t panels = (k + kNB - 1) / kNB;
   mg::CholStepper chol{w.ckk, k, kp, w.chol, info, &L};
-  // ---- forward solve  U^T Z = rhs  (right-looking, in place) rides one panel behind the
-  //      factorisation on the tri lane: step pi needs block row pi of U and nothing later
-  //      Two-level blocking like the factorisation: inside an outer block of kFwdOuter panels a
-  //      panel only updates the block's remaining rows (K = 128); the rows below the block get one
-  //      update per block with K = kFwdOuter * 128 from the block's stacked Z planes — a quarter
-  //      of the read-modify-write passes over rhs.
-  constexpr int64_t kFwdOuter = 4;
-  const int64_t zb_stride = kFwdOuter * kNB * dp;      // plane stride of the stacked Z block
-  for (int64_t pi = 0; pi < panels; ++pi) {
-    if ((rc = chol.step(pi))) return rc;
-    L.wait(L.tri, L.trsm);
-    const int64_t i0 = pi * kNB;
-    const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
-    float* bi = w.rhs + i0 * dp;
-    const int64_t rest = k - i0 - nb;
-    const int64_t q = pi % kFwdOuter, o0 = (pi - q) * kNB;
-    const int64_t o_end = (o0 + kFwdOuter * kNB < k) ? o0 + kFwdOuter * kNB : k;
-    bf16* zq = w.zb_planes + q * kNB * dp;              // this panel's rows inside the Z block
-    // Z_i = U_ii^-T B_i (+ planes of Z_i for the updates below)
-    MG_TIMED(L.tri, "nystrom.fwd_trsm",
-             rc = mg::trsm128(w.chol.t_fwd + pi * mg::kTBlock, false, nb, bi, dp, d, 1.f, bi, dp,
-                              rest > 0 ? zq : nullptr, dp, zb_stride, nullptr, 0, 0, nullptr, L.tri));
-    if (rc) return rc;
-    if (rest <= 0) break;
-    mg::GemmArgs t{};
-    t.lda = kp;
-    t.a_plane_stride = pstride;
-    t.a_planes = kPlanes;
-    t.ldb = dp;
-    t.b_plane_stride = zb_stride;
-    t.b_planes = kPlanes;
-    pairs6(t);
-    t.N = d;
-    t.ldd = dp;
-    t.alpha = -1.f;
-    t.tiles = mg::TILES_FULL;
-    t.epi = mg::EPI_ADD;
-    t.ksplit = 1;
-    t.max_ctas = L.bulk_cta_cap();
-    const int64_t in_block = o_end - (i0 + nb);
-    if (in_block > 0) {            // B[block rows below] -= U[ib, those rows]^T Z_i
-      t.A = w.chol.u_planes + i0 * kp + (i0 + nb);
-      t.B = zq;
-      t.M = in_block;
-      t.K = nb;
-      t.D = w.rhs + (i0 + nb) * dp;
-      MG_TIMED(L.tri, "nystrom.fwd_update_in_block", rc = mg::gemm_tn_launch(t, L.tri));
-    } else {                       // B[rows below the block] -= U[block rows, those rows]^T Z_block
-      t.A = w.chol.u_planes + o0 * kp + o_end;
-      t.B = w.zb_planes;
-      t.M = rest;
-      t.K = o_end - o0;
-      t.D = w.rhs + o_end * dp;
-      MG_TIMED(L.tri, "nystrom.fwd_update", rc = mg::gemm_tn_launch(t, L.tri));
-    }
-    if (rc) return rc;
+  if ((rc = nystrom_solves(w, L, k, d, &chol))) return rc;
+  // conditioning indicator: min_i U_ii^2 / A_ii (1 / (A_ii (A^-1)_ii) for the last pivot; small
+  // values announce an ill-conditioned EQUILIBRATED system — the raw diagonal spread is harmless)
+  if (min_rel_pivot) {
+    set_float_kernel<<<1, 1, 0, L.chain>>>(min_rel_pivot, 3.0e38f);
+    min_rel_pivot_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, L.chain>>>(
+        C, ldc, idx, k, w.ckk, kp, jitter, min_rel_pivot);
+    if ((rc = cuda_rc())) return rc;
   }
-  // ---- backward solve  U X = Z  on the chain lane, once the forward pass and every trailing
-  //      update have landed
-  L.record(L.misc[0], L.tri);
-  L.wait(L.chain, L.misc[0]);
-  L.record(L.misc[1], L.upd);
-  L.wait(L.chain, L.misc[1]);
-  L.record(L.row_rest[0], L.chain2);
-  L.wait(L.chain, L.row_rest[0]);
-  //      Two-level blocking + look-ahead, mirrored from the factorisation (panels run from the
-  //      last to the first): inside an outer block a panel only updates the block's rows above it
-  //      (K = 128, chain lane); when the block's first panel is solved, the rows above the block
-  //      get the whole block at once (K = 512) — the next block's last block row on the chain
-  //      lane, its other rows and everything above on the upd lane.
-  if (L.serial) {
-    for (int64_t pi = panels - 1; pi >= 0; --pi) {
-      const int64_t i0 = pi * kNB;
-      const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
-      float* zi = w.rhs + i0 * dp;
-      MG_TIMED(L.chain, "nystrom.bwd_trsm",
-               rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
-                                i0 > 0 ? w.z_planes : nullptr, dp, kNB * dp, nullptr, 0, 0, nullptr,
-                                L.chain));
-      if (rc) return rc;
-      if (i0 == 0) break;
-      mg::GemmArgs t{};
-      t.A = w.chol.l_planes + i0 * kp;   // Z[0:i0] -= U[0:i0, ib] X_i, A[k, m] = L[i0 + k, m]
-      t.lda = kp;
-      t.a_plane_stride = pstride;
-      t.a_planes = kPlanes;
-      t.B = w.z_planes;
-      t.ldb = dp;
-      t.b_plane_stride = kNB * dp;
-      t.b_planes = kPlanes;
-      pairs6(t);
-      t.M = i0;
-      t.N = d;
-      t.K = nb;
-      t.D = w.rhs;
-      t.ldd = dp;
-      t.alpha = -1.f;
-      t.tiles = mg::TILES_FULL;
-      t.epi = mg::EPI_ADD;
-      t.ksplit = 1;
-      MG_TIMED(L.chain, "nystrom.bwd_update", rc = mg::gemm_tn_launch(t, L.chain));
-      if (rc) return rc;
-    }
-  } else {
-    const int64_t nblocks = (panels + kFwdOuter - 1) / kFwdOuter;
-    for (int64_t pi = panels - 1; pi >= 0; --pi) {
-      const int64_t i0 = pi * kNB;
-      const int nb = static_cast<int>(k - i0 < kNB ? k - i0 : kNB);
-      const int64_t ob = pi / kFwdOuter, o0 = ob * kFwdOuter * kNB;
-      const int64_t o_end = (o0 + kFwdOuter * kNB < k) ? o0 + kFwdOuter * kNB : k;
-      // X planes of the block, stacked by row (double-buffered by block parity: the upd lane may
-      // still read block ob while the chain lane fills block ob-1)
-      bf16* xb = w.xb_planes + (ob & 1) * kPlanes * zb_stride;
-      bf16* xq = xb + (i0 - o0) * dp;
-      float* zi = w.rhs + i0 * dp;
-      MG_TIMED(L.chain, "nystrom.bwd_trsm",
-               rc = mg::trsm128(w.chol.t_bwd + pi * mg::kTBlock, true, nb, zi, dp, d, 1.f, zi, dp,
-                                i0 > 0 ? xq : nullptr, dp, zb_stride, nullptr, 0, 0, nullptr, L.chain));
-      if (rc) return rc;
-      if (i0 == 0) break;
-      mg::GemmArgs t{};
-      t.lda = kp;
-      t.a_plane_stride = pstride;
-      t.a_planes = kPlanes;
-      t.ldb = dp;
-      t.b_plane_stride = zb_stride;
-      t.b_planes = kPlanes;
-      pairs6(t);
-      t.N = d;
-      t.ldd = dp;
-      t.alpha = -1.f;
-      t.tiles = mg::TILES_FULL;
-      t.epi = mg::EPI_ADD;
-      t.ksplit = 1;
-      const int64_t above = i0 - o0;                  // rows of this block above panel pi
-      if (above > 0) {
-        // (ordered adds) the block below updated these rows from the upd lane
-        if (i0 + nb >= o_end && ob + 1 < nblocks) L.wait(L.chain, L.next_done[(ob + 1) & 1]);
-        t.A = w.chol.l_planes + i0 * kp + o0;         // A[k, m] = L[i0 + k, o0 + m] = U[o0 + m, i0 + k]
-        t.B = xq;
-        t.M = above;
-        t.K = nb;
-        t.D = w.rhs + o0 * dp;
-        MG_TIMED(L.chain, "nystrom.bwd_update_in_block", rc = mg::gemm_tn_launch(t, L.chain));
-        if (rc) return rc;
-        continue;
-      }
-      // pi is the block's first panel: rows [0, o0) get the whole block (K = o_end - o0)
-      t.K = o_end - o0;
-      t.B = xb;
-      const int64_t first = kNB;                      // o0 is a multiple of 4 * 128
-      const int64_t next_rows = kFwdOuter * kNB;      // rows of the block above (all of them exist)
-      L.record(L.trsm, L.chain);
-      L.wait(L.upd, L.trsm);
-      {
-        mg::GemmArgs r = t;                           // block above, except its last block row
-        r.A = w.chol.l_planes + o0 * kp + (o0 - next_rows);
-        r.M = next_rows - first;
-        r.D = w.rhs + (o0 - next_rows) * dp;
-        r.max_ctas = L.bulk_cta_cap();
-        MG_TIMED(L.upd, "nystrom.bwd_update_next", rc = mg::gemm_tn_launch(r, L.upd));
-        if (rc) return rc;
-        L.record(L.next_done[ob & 1], L.upd);
-      }
-      if (o0 - next_rows > 0) {                       // everything above that block
-        mg::GemmArgs r = t;
-        r.A = w.chol.l_planes + o0 * kp;
-        r.M = o0 - next_rows;
-        r.D = w.rhs;
-        r.max_ctas = L.bulk_cta_cap();
-        MG_TIMED(L.upd, "nystrom.bwd_update", rc = mg::gemm_tn_launch(r, L.upd));
-        if (rc) return rc;
-      }
-      L.record(L.upd_done[ob & 1], L.upd);
-      // chain: the last block row of the block above (the next panel to be solved)
-      if (ob + 1 < nblocks) L.wait(L.chain, L.upd_done[(ob + 1) & 1]);
-      t.A = w.chol.l_planes + o0 * kp + (o0 - first);
-      t.M = first;
-      t.D = w.rhs + (o0 - first) * dp;
-      MG_TIMED(L.chain, "nystrom.bwd_update_first", rc = mg::gemm_tn_launch(t, L.chain));
-      if (rc) return rc;
-    }
-  }
-  // ---- W_down' [d, k] = (W_down[:, idx]^T + X)^T, bf16
+  // ---- xacc = W_down[:, idx]^T + X (fp32, kept for mg_nystrom_refine_f32);  W_down' [d, k] = xacc^T, bf16
   L.record(L.misc[0], L.tri);      // wdt was produced on the tri lane
   L.wait(L.chain, L.misc[0]);
-  add_kept_transpose_kernel<<<dim3(static_cast<unsigned>((d + 31) / 32),
-                                   static_cast<unsigned>((k + 31) / 32)),
-                              256, 0, L.chain>>>(w.rhs, dp, w.wdt, dp, idx, k, d,
-                                                 static_cast<bf16*>(Wd_out), ld_out);
+  add_kept_rows_kernel<<<static_cast<unsigned>(k), 256, 0, L.chain>>>(w.rhs, dp, w.wdt, dp, idx, d, w.xacc, 0);
+  if ((rc = cuda_rc())) return rc;
+  transpose_to_bf16_kernel<float><<<dim3(static_cast<unsigned>((d + 31) / 32),
+                                         static_cast<unsigned>((k + 31) / 32)),
+                                    256, 0, L.chain>>>(w.xacc, dp, k, d, static_cast<bf16*>(Wd_out), ld_out);
   rc = cuda_rc();
   mg::Prof::get().report(s, "mg_nystrom_down_f32");
   return rc;
+}
+
+int mg_nystrom_refine_f32(const float* C, int64_t n, int64_t ldc, const int64_t* idx, int64_t k,
+                          int64_t d, float jitter, void* Wd_out, int64_t ld_out, void* ws,
+                          size_t ws_bytes, void* stream) {
+  if (!C || !idx || !Wd_out || !ws) return -1;
+  if (n <= 0 || k <= 0 || k > n || d <= 0) return -2;
+  if (ldc < n || ld_out < k) return -7;
+  NystromWs w = carve_nystrom(ws, n, k, d);
+  if (ws_bytes < w.bytes) return -10;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dp = mg::round_up(d, 64);
+  int rc;
+  // fp64 residual of the current solution -> fp32 right-hand side of the correction
+  nystrom_resid64_kernel<<<dim3(static_cast<unsigned>((k + 127) / 128), static_cast<unsigned>((d + 127) / 128)),
+                           256, 0, s>>>(C, ldc, n, idx, k, w.wdt, dp, w.pos, w.xacc, dp, d, jitter, w.rhs);
+  if ((rc = cuda_rc())) return rc;
+  {
+    mg::LaneScope scope(s, k);
+    if ((rc = nystrom_solves(w, scope.lanes(), k, d, nullptr))) return rc;
+  }
+  add_kept_rows_kernel<<<static_cast<unsigned>(k), 256, 0, s>>>(w.rhs, dp, w.wdt, dp, idx, d, w.xacc, 1);
+  if ((rc = cuda_rc())) return rc;
+  transpose_to_bf16_kernel<float><<<dim3(static_cast<unsigned>((d + 31) / 32),
+                                         static_cast<unsigned>((k + 31) / 32)),
+                                    256, 0, s>>>(w.xacc, dp, k, d, static_cast<bf16*>(Wd_out), ld_out);
+  return cuda_rc();
 }
 
 }  // extern "C"

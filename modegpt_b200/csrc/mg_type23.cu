@@ -397,9 +397,51 @@ __global__ void copy_upper_ridge_kernel(const float* __restrict__ src, int64_t l
   }
 }
 
+// In-place Cholesky of the symmetric positive definite matrix in s.g (fp64, [hd][hd+1]): on success
+// the LOWER triangle holds L (G = L L^T), the strict upper triangle is stale.  Right-looking, one
+// pivot per round, all threads update the trailing block (hd <= 128: ~40 us).  Returns false —
+// leaving s.g unusable — if a pivot is not safely positive (G numerically singular in fp64).
+__device__ bool chol_lower_inplace(double* g, int ld, int hd, double* red) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  __shared__ int s_ok;
+  __shared__ double s_scale;
+  if (t == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < hd; ++i) mx = fmax(mx, g[i * ld + i]);
+    s_scale = mx;
+    s_ok = 1;
+  }
+  __syncthreads();
+  const double floor_piv = 1e-13 * s_scale;
+  for (int j = 0; j < hd; ++j) {
+    if (t == 0) {
+      const double piv = g[j * ld + j];
+      if (!(piv > floor_piv)) s_ok = 0;
+      red[0] = piv > floor_piv ? rsqrt(piv) : 0.0;
+    }
+    __syncthreads();
+    if (!s_ok) return false;
+    const double inv = red[0];
+    // column j of L (rows j..hd-1): g[i][j] = g[i][j] / sqrt(piv); the lower triangle is kept current
+    for (int i = j + t; i < hd; i += nt) g[i * ld + j] *= inv;
+    __syncthreads();
+    // trailing update of the lower triangle: g[i][k] -= L[i][j] L[k][j] for j < k <= i
+    const int m = hd - j - 1;
+    for (int e = t; e < m * m; e += nt) {
+      const int ii = e / m, kk = e - ii * m;
+      if (kk <= ii) {
+        const int i = j + 1 + ii, k = j + 1 + kk;
+        g[i * ld + k] = fma(-g[i * ld + j], g[k * ld + j], g[i * ld + k]);
+      }
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
 // One CTA per kv head.
 //   G1 [KV][n1][hd*hd] fp64 partial sums, G2 [H][n2][hd*hd] fp64 (MHA only, may be null),
-//   scratch [KV][2][hd*hd] fp32, Rv, Ro [KV][hd, r] fp32.
+//   scratch [KV][4][hd*hd] fp32 (per head: D in fp32, T in fp64), Rv, Ro [KV][hd, r] fp32.
 __global__ void __launch_bounds__(1024, 1)
     vo_factor_kernel(const double* __restrict__ G1, int n1, const double* __restrict__ G2, int n2,
                      int hd, int r, float* __restrict__ scratch, float* __restrict__ Rv,
@@ -427,10 +469,10 @@ __global__ void __launch_bounds__(1024, 1)
     s.g[i * ld + k] = isfinite(gsym) ? gsym : 0.0;
   }
   __syncthreads();
-  jacobi_eig(s, hd);
 
   if (G2 == nullptr) {
     // GQA: Rv = V_r S_r^-1, Ro = V_r S_r
+    jacobi_eig(s, hd);
     for (int e = t; e < hd * r; e += nt) {
       const int i = e / r, a = e - i * r;
       const int col = s.perm[a];
@@ -442,23 +484,46 @@ __global__ void __launch_bounds__(1024, 1)
     return;
   }
 
-  // ---- MHA second stage
+  // ---- MHA.  The reference's second SVD acts on A = S V^T W_o^T, i.e. on B = D^T G2 D with
+  // D = V S.  ANY D with D D^T = G1 serves: D' = D Q (Q orthogonal) turns B into Q^T B Q, its
+  // eigenvectors into Q^T U_p, and leaves Ro = D U_p[:, :r] unchanged.  Taking the Cholesky factor
+  // D = L (G1 = L L^T, ~40 us) replaces the FIRST of the two Jacobi eigensolves (~4 ms); the
+  // eigensolve of G1 stays as the fallback for a G1 that is singular in fp64.
   const double* g2 = G2 + static_cast<int64_t>(h) * n2 * hh;
-  float* vg = scratch + static_cast<int64_t>(h) * 2 * hh;       // V (sorted columns)
-  double* sval = s.cs;  // singular values S (sorted), reuse the rotation buffer
-  if (t < hd) sval[t] = sqrt(fmax(s.lam[s.perm[t]], 0.0));
-  for (int e = t; e < hh; e += nt) {
-    const int i = e / hd, a = e - i * hd;
-    vg[e] = s.v[i * ldv + s.perm[a]];
+  float* vg = scratch + static_cast<int64_t>(h) * 4 * hh;       // D in fp32 (survives the eigensolve)
+  double* tg = reinterpret_cast<double*>(vg + hh);              // T = G2 D in fp64 (global, L2-resident)
+  if (chol_lower_inplace(s.g, ld, hd, s.red)) {
+    for (int e = t; e < hh; e += nt) {       // D = L: clear the stale strict upper triangle
+      const int i = e / hd, a = e - i * hd;
+      if (a > i) s.g[i * ld + a] = 0.0;
+    }
+  } else {
+    for (int e = t; e < hh; e += nt) {       // reload G1 (the failed factorisation overwrote it)
+      const int i = e / hd, k = e - i * hd;
+      double x = 0.0, y = 0.0;
+      for (int p = 0; p < n1; ++p) {
+        x += g1[p * hh + i * hd + k];
+        y += g1[p * hh + k * hd + i];
+      }
+      const double gsym = 0.5 * (x + y);
+      s.g[i * ld + k] = isfinite(gsym) ? gsym : 0.0;
+    }
+    __syncthreads();
+    jacobi_eig(s, hd);
+    double* sval = s.cs;  // singular values S (sorted), reuse the rotation buffer
+    if (t < hd) sval[t] = sqrt(fmax(s.lam[s.perm[t]], 0.0));
+    __syncthreads();
+    for (int e = t; e < hh; e += nt) {       // D = V S, columns in descending order (s.g is free now)
+      const int i = e / hd, a = e - i * hd;
+      s.g[i * ld + a] = static_cast<double>(s.v[i * ldv + s.perm[a]]) * sval[a];
+    }
   }
   __syncthreads();
-  // D = V S in shared memory (overwrites v, sorted order)
   for (int e = t; e < hh; e += nt) {
     const int i = e / hd, a = e - i * hd;
-    s.v[i * ldv + a] = static_cast<float>(static_cast<double>(vg[e]) * sval[a]);
+    vg[e] = static_cast<float>(s.g[i * ld + a]);
   }
-  __syncthreads();
-  // T = G2 D   (fp64, kept in the fp64 buffer: s.g is free until B is formed)
+  // T = G2 D   (fp64, through global memory: shared memory holds D and has no room for T)
   for (int e = t; e < hh; e += nt) {
     const int i = e / hd, a = e - i * hd;
     double acc = 0.0;
@@ -468,12 +533,12 @@ __global__ void __launch_bounds__(1024, 1)
         x += g2[p * hh + i * hd + k];
         y += g2[p * hh + k * hd + i];
       }
-      acc += 0.5 * (x + y) * static_cast<double>(s.v[k * ldv + a]);
+      acc += 0.5 * (x + y) * s.g[k * ld + a];
     }
-    s.g[i * ld + a] = acc;
+    tg[e] = acc;
   }
   __syncthreads();
-  // B = D^T T  (symmetric): computed into registers first (s.g holds T), then written back
+  // B = D^T T  (symmetric): computed into registers first (s.g holds D), then written back
   {
     constexpr int kPer = kMaxHd * kMaxHd / 1024;   // elements per thread at hd = 128
     double bacc[kPer];
@@ -483,8 +548,7 @@ __global__ void __launch_bounds__(1024, 1)
       double acc = 0.0;
       if (e < hh) {
         const int a = e / hd, b = e - a * hd;
-        for (int k = 0; k < hd; ++k)
-          acc += static_cast<double>(s.v[k * ldv + a]) * s.g[k * ld + b];
+        for (int k = 0; k < hd; ++k) acc += s.g[k * ld + a] * tg[k * hd + b];
       }
       bacc[c] = acc;
     }
@@ -507,23 +571,19 @@ __global__ void __launch_bounds__(1024, 1)
       s.g[b * ld + a] = x;
     }
   }
-  // keep S: jacobi_eig overwrites cs
-  __shared__ double s_keep[kMaxHd];
-  if (t < hd) s_keep[t] = sval[t];
   __syncthreads();
   jacobi_eig(s, hd);  // s.v now holds U_p (unsorted columns), perm the descending order
-  // Ro = V S U_p[:, :r].  Rv = V S^-1 U_p[:, :r] is NOT formed by dividing: the components of the
-  // leading eigenvectors u_a along the small singular directions are tiny (~sigma_k / sigma_1) and
-  // carry only the eigensolver's absolute accuracy, so sigma_k^-1 u_a[k] would amplify its
-  // rounding by sigma_1 / sigma_k.  From B u = lambda u with B = S M S, M = V^T G2 V:
-  //     S^-1 u = M (S u) / lambda     =>     Rv = V S^-1 U_r = G2 (V S U_r) Lambda_r^-1 = G2 Ro Lambda_r^-1,
+  // Ro = D U_p[:, :r].  Rv = D^-T U_p[:, :r] (= V S^-1 U_p[:, :r] for D = V S) is NOT formed through
+  // D^-1: the components of the leading eigenvectors along the small singular directions are tiny
+  // and carry only the eigensolver's absolute accuracy.  From B u = lambda u with B = D^T G2 D:
+  //     D^-T u = G2 (D u) / lambda     =>     Rv = G2 Ro Lambda_r^-1,
   // which only ever divides by the r LARGEST eigenvalues of B.
   for (int e = t; e < hd * r; e += nt) {
     const int i = e / r, a = e - i * r;
     const int col = s.perm[a];
     double ao = 0.0;
     for (int k = 0; k < hd; ++k)
-      ao += static_cast<double>(vg[i * hd + k]) * s_keep[k] * static_cast<double>(s.v[k * ldv + col]);
+      ao += static_cast<double>(vg[i * hd + k]) * static_cast<double>(s.v[k * ldv + col]);
     ro[e] = static_cast<float>(ao);
   }
   __syncthreads();     // ro (global, written by this CTA) is read back below
@@ -654,7 +714,7 @@ struct VoWs {
   double* g1;       // [KV][parts][hd*hd]
   float* g2f;       // [H, hd, hd]    tensor-core W_o,h^T W_o,h (hd in {32, 64, 128})
   double* g2;       // [H][parts][hd*hd]
-  float* scratch;   // [KV][2][hd*hd]
+  float* scratch;   // [KV][4][hd*hd]  per head: D fp32, T fp64
   float* rv;        // [KV][hd, r<=hd]
   float* ro;
   size_t bytes;
@@ -691,7 +751,7 @@ VoWs carve_vo(void* ptr, int64_t d, int H, int KV, int hd) {
   w.g1 = c.take<double>(static_cast<size_t>(KV) * gram_parts(KV) * hh);
   w.g2f = c.take<float>(static_cast<size_t>(H) * hh);
   w.g2 = c.take<double>(static_cast<size_t>(H) * gram_parts(H) * hh);
-  w.scratch = c.take<float>(static_cast<size_t>(KV) * 2 * hh);
+  w.scratch = c.take<float>(static_cast<size_t>(KV) * 4 * hh);
   w.rv = c.take<float>(static_cast<size_t>(KV) * hh);
   w.ro = c.take<float>(static_cast<size_t>(KV) * hh);
   w.bytes = c.off + 256;

@@ -179,9 +179,20 @@ def gather_rows(W: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def nystrom_down(C: torch.Tensor, idx: torch.Tensor, Wd: torch.Tensor,
-                 jitter: float = 1e-6) -> torch.Tensor:
-    """((C[idx,idx] + jitter I)^-1 C[idx,:] Wd^T)^T as bf16 [d, k]; C full symmetric float32."""
+# refine automatically when the fp32 solve is expected to miss ~1e-4 (error ~ 1e-7 / min_rel_pivot),
+# and always when a sweep is nearly free (small models)
+REFINE_BELOW_PIVOT = 2e-3
+REFINE_FREE_FLOPS = 5e10
+
+
+def nystrom_down(C: torch.Tensor, idx: torch.Tensor, Wd: torch.Tensor, jitter: float = 1e-6,
+                 refine: bool | str = "auto", stats: dict | None = None) -> torch.Tensor:
+    """((C[idx,idx] + jitter I)^-1 C[idx,:] Wd^T)^T as bf16 [d, k]; C full symmetric float32.
+
+    refine: "auto" (default) runs fp64-residual refinement sweeps when the Cholesky factor's
+    smallest relative pivot says the fp32 solve is not enough, or when a sweep costs next to
+    nothing; True forces one sweep, False none.  `stats` (optional dict) receives the indicator and
+    the number of sweeps."""
     n, ldc = _f32_square(C, "C")
     d, n2, ldwd = _rowmajor_2d(Wd, "Wd")
     if n2 != n or Wd.dtype != torch.bfloat16:
@@ -189,15 +200,29 @@ def nystrom_down(C: torch.Tensor, idx: torch.Tensor, Wd: torch.Tensor,
     k = idx.numel()
     out = torch.empty(d, k, dtype=torch.bfloat16, device=C.device)
     info = torch.zeros(1, dtype=torch.int32, device=C.device)
+    pivot = torch.zeros(1, dtype=torch.float32, device=C.device)
     nbytes = lib.mg_nystrom_down_ws_bytes(n, k, d)
     ws = _workspace(nbytes, C.device)
     check("mg_nystrom_down_f32",
           lib.mg_nystrom_down_f32(C.data_ptr(), n, ldc, idx.data_ptr(), k, Wd.data_ptr(), d, ldwd,
                                   jitter, out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes,
-                                  info.data_ptr(), _stream()))
+                                  info.data_ptr(), pivot.data_ptr(), _stream()))
     piv = int(info.item())
     if piv:
         raise NotPositiveDefinite("nystrom_down", piv)
+    rel_pivot = float(pivot.item())
+    if refine == "auto":
+        sweeps = 0
+        if rel_pivot < REFINE_BELOW_PIVOT or 2.0 * k * n * d < REFINE_FREE_FLOPS:
+            sweeps = 2 if rel_pivot < 2e-5 else 1
+    else:
+        sweeps = 1 if refine else 0
+    for _ in range(sweeps):
+        check("mg_nystrom_refine_f32",
+              lib.mg_nystrom_refine_f32(C.data_ptr(), n, ldc, idx.data_ptr(), k, d, jitter, out.data_ptr(),
+                                        out.stride(0), ws.data_ptr(), nbytes, _stream()))
+    if stats is not None:
+        stats.update(min_rel_pivot=rel_pivot, refine_sweeps=sweeps)
     return out
 
 

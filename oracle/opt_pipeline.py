@@ -40,51 +40,57 @@ def run(model, batches: list[torch.Tensor], compression_ratio: float, nystrom_ri
     L, H, d = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.hidden_size
     hd = d // H
     dec = model.model.decoder
-    cap = {k: [[] for _ in range(L)] for k in ("fc2_in", "ln_out", "q_out", "k_out", "blk_in", "blk_out")}
-    final = []
+    # statistics are accumulated batch by batch inside the hooks (raw sums, normalised below);
+    # only the current batch's block inputs / outputs are kept, for the Block-Influence pairs
+    acc = {"mlp": [0.0] * L, "x": [0.0] * L, "q": [0.0] * L, "k": [0.0] * L}
+    cur: dict = {}
     handles = []
     f64 = lambda t: t.detach().to(torch.float64).numpy()
+
+    def add(key, i, value):
+        acc[key][i] = acc[key][i] + value
+
     for i, blk in enumerate(dec.layers):
         handles.append(blk.fc2.register_forward_pre_hook(
-            lambda m, inp, i=i: cap["fc2_in"][i].append(f64(inp[0]))))
+            lambda m, inp, i=i: add("mlp", i, O.gram_rows(f64(inp[0])))))
         handles.append(blk.self_attn_layer_norm.register_forward_hook(
-            lambda m, inp, out, i=i: cap["ln_out"][i].append(f64(out))))
+            lambda m, inp, out, i=i: add("x", i, O.gram_rows(f64(out)))))
         handles.append(blk.self_attn.q_proj.register_forward_hook(
-            lambda m, inp, out, i=i: cap["q_out"][i].append(f64(out))))
+            lambda m, inp, out, i=i: add("q", i, O.gram_heads(f64(out), H, hd))))
         handles.append(blk.self_attn.k_proj.register_forward_hook(
-            lambda m, inp, out, i=i: cap["k_out"][i].append(f64(out))))
+            lambda m, inp, out, i=i: add("k", i, O.gram_heads(f64(out), H, hd))))
         handles.append(blk.register_forward_pre_hook(
-            lambda m, args, kwargs, i=i: cap["blk_in"][i].append(f64(args[0] if args else kwargs["hidden_states"])),
+            lambda m, args, kwargs, i=i: cur.__setitem__(("in", i), f64(args[0] if args else kwargs["hidden_states"])),
             with_kwargs=True))
         handles.append(blk.register_forward_hook(
-            lambda m, args, out, i=i: cap["blk_out"][i].append(f64(out[0] if isinstance(out, (tuple, list)) else out))))
-    handles.append(dec.final_layer_norm.register_forward_hook(lambda m, inp, out: final.append(f64(out))))
+            lambda m, args, out, i=i: cur.__setitem__(("out", i), f64(out[0] if isinstance(out, (tuple, list)) else out))))
+    handles.append(dec.final_layer_norm.register_forward_hook(lambda m, inp, out: cur.__setitem__("final", f64(out))))
+    bi = np.zeros(L)
     try:
         for b in batches:
+            cur.clear()
             model.model(b, use_cache=False)
+            B = b.shape[0]
+            for l in range(L):
+                x_out = cur["final"] if l == L - 1 else cur[("out", l)]
+                bi[l] += O.bi_batch(cur[("in", l)].reshape(B, -1, d), x_out.reshape(B, -1, d))
     finally:
         for h in handles:
             h.remove()
+    cur.clear()
 
     n_texts = sum(len(b) for b in batches)
     out: dict = {"n_texts": n_texts}
-    bi = np.zeros(L)
-    for bidx in range(len(batches)):
-        for l in range(L):
-            x_in = cap["blk_in"][l][bidx]
-            x_out = final[bidx] if l == L - 1 else cap["blk_out"][l][bidx]
-            B = batches[bidx].shape[0]
-            bi[l] += O.bi_batch(x_in.reshape(B, -1, d), x_out.reshape(B, -1, d))
     bi /= n_texts
     keep = O.allocate_global_sparsity(bi, compression_ratio, smoothing, max_sparsity)
     out["bi"], out["keep"] = bi, np.array(keep)
     sd = {k: v.detach().float().numpy() for k, v in model.state_dict().items()}
     for l in range(L):
         pre = f"model.decoder.layers.{l}."
-        c_mlp = O.normalise_stats(sum(O.gram_rows(a) for a in cap["fc2_in"][l]), n_texts)
-        c_x = O.normalise_stats(sum(O.gram_rows(a) for a in cap["ln_out"][l]), n_texts)
-        c_q = O.normalise_stats(sum(O.gram_heads(a, H, hd) for a in cap["q_out"][l]), n_texts)
-        c_k = O.normalise_stats(sum(O.gram_heads(a, H, hd) for a in cap["k_out"][l]), n_texts)
+        c_mlp = O.normalise_stats(acc["mlp"][l], n_texts)
+        c_x = O.normalise_stats(acc["x"][l], n_texts)
+        c_q = O.normalise_stats(acc["q"][l], n_texts)
+        c_k = O.normalise_stats(acc["k"][l], n_texts)
         out[f"cov_mlp{l}"], out[f"cov_x{l}"], out[f"cov_q{l}"], out[f"cov_k{l}"] = c_mlp, c_x, c_q, c_k
         # type I
         mlp, idx, rank = O.nystrom_mlp(sd[pre + "fc1.weight"], None, sd[pre + "fc2.weight"], c_mlp, keep[l],

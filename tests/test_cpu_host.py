@@ -207,3 +207,45 @@ def test_layer_writer_files_match_blocking_save(tmp_path):
     with pytest.raises(RuntimeError):
         w.flush()
     w.close()
+
+
+def test_fp16_checkpoint_is_cast_to_bf16_at_load(tmp_path):
+    """facebook/opt-* and Llama-2-*-hf ship fp16 weights; the kernels take bf16 only.  The loader
+    casts once instead of failing at the first calibration hook."""
+    import torch
+    from transformers import AutoModelForCausalLM, LlamaConfig
+
+    from modegpt_b200.adapters.model_adapter import ModelAdapter
+    from modegpt_b200.model_utils import reload_compressed_model
+
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, head_dim=16, vocab_size=96, max_position_embeddings=64,
+                      tie_word_embeddings=False)
+    model = AutoModelForCausalLM.from_config(cfg).to(torch.float16)
+    model.save_pretrained(tmp_path / "fp16")
+    loaded, _ = reload_compressed_model(str(tmp_path / "fp16"), device="cpu", tokenizer_source="synthetic:none")
+    assert {p.dtype for p in loaded.parameters()} == {torch.bfloat16}
+    adapter = ModelAdapter.from_model(loaded, tokenizer=None)
+    adapter.validate_for_kernels()
+    bad = AutoModelForCausalLM.from_config(cfg).to(torch.float16)
+    with pytest.raises(TypeError):
+        ModelAdapter.from_model(bad, tokenizer=None).validate_for_kernels()
+
+
+def test_layer_streamed_flow_refuses_eager_attention():
+    """With attention_mask=None HF's eager attention is bidirectional: the streamed calibration
+    must not silently compute different statistics."""
+    from modegpt_b200.adapters.CompressionConfig import CompressionConfig
+    from modegpt_b200.adapters.model_adapter import ModelAdapter
+    from modegpt_b200.calibration import _LayerStepper
+    from modegpt_b200.model_utils import build_synthetic_model
+
+    model = build_synthetic_model("tiny-llama", device="cpu", max_positions=64)
+    adapter = ModelAdapter.from_model(model, tokenizer=None)
+    adapter.config = CompressionConfig(model="tiny", dataset="synthetic", calib_size=2, calibs_batch_size=2,
+                                       seq_len=32)
+    model.config._attn_implementation = "eager"
+    with pytest.raises(NotImplementedError):
+        _LayerStepper(adapter, "synthetic")
+    model.config._attn_implementation = "sdpa"
+    _LayerStepper(adapter, "synthetic")
