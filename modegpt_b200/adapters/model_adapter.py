@@ -404,7 +404,9 @@ class ModelAdapter(ABC):
         # one pool buffer holds the largest tensor a layer can produce (an uncompressed MLP matrix)
         largest = 2 * self.d_model * max(self.get_n_inner(), self.n_heads * self.head_dim)
         self._writer = LayerWriter(device=next(self.model.parameters()).device,
-                                   pool_buffer_bytes=(largest + 4095) // 4096 * 4096)
+                                   pool_buffer_bytes=(largest + 4095) // 4096 * 4096,
+                                   n_threads=int(os.environ.get("MG_WRITER_SAVERS", "8")),
+                                   n_stagers=int(os.environ.get("MG_WRITER_STAGERS", "3")))
 
     def flush_saves(self) -> None:
         """Block until every submitted layer file is on disk (raises if a write failed)."""

@@ -118,13 +118,15 @@ class LayerWriter:
 
     # ------------------------------------------------------------------------------------------
     def _stager(self) -> None:
+        # The stream is created up front; the two 64 MB bounce buffers of the fallback route only
+        # when a tensor actually needs them: pinning memory (cudaHostAlloc) stalls every other CUDA
+        # call of the process while it runs, and three stager threads pinning 384 MB right after
+        # `prepare_writer()` returned cost the FIRST decomposition stage of a run ~10 ms per layer.
         stream, bounce, events = None, None, None
         if self._warm_device is not None and self._warm_device.type == "cuda":
             try:
                 torch.cuda.set_device(self._warm_device)   # threads start on device 0: keep rank r on GPU r
                 stream = torch.cuda.Stream(device=self._warm_device)
-                bounce = [torch.empty(_SLICE, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-                events = [torch.cuda.Event() for _ in range(2)]
             except BaseException as e:
                 self._errors.append(e)
                 stream = None
@@ -141,8 +143,6 @@ class LayerWriter:
                     if stream is None or stream.device != dev:
                         torch.cuda.set_device(dev)
                         stream = torch.cuda.Stream(device=dev)
-                        bounce = [torch.empty(_SLICE, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-                        events = [torch.cuda.Event() for _ in range(2)]
                     with torch.cuda.stream(stream):
                         stream.wait_event(ready)
                         t0 = time.perf_counter()
@@ -150,9 +150,16 @@ class LayerWriter:
                         t1 = time.perf_counter()
                         self._add("pool_wait_s", t1 - t0)
                         held = list(bufs.values())
-                        weights = {k: (self._to_pinned(w, bufs[k], stream) if k in bufs
-                                       else self._to_host(w, stream, bounce, events))
-                                   for k, w in weights.items()}
+                        staged = {}
+                        for k, w in weights.items():
+                            if k in bufs:
+                                staged[k] = self._to_pinned(w, bufs[k], stream)
+                            else:
+                                if w.is_cuda and bounce is None:
+                                    bounce = [torch.empty(_SLICE, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+                                    events = [torch.cuda.Event() for _ in range(2)]
+                                staged[k] = self._to_host(w, stream, bounce, events)
+                        weights = staged
                         if held:
                             stream.synchronize()
                         self._add("stage_s", time.perf_counter() - t1)

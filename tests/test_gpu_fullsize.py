@@ -53,9 +53,11 @@ def test_syrk_7b_mlp_shape_blocks_linearity_symmetry(ops, c_mlp):
     assert rel(whole, c) < 1e-4
 
 
-@pytest.mark.parametrize("n,T,H,hd", [(14336, 4096, 32, 128), (28672, 2048, 64, 128), (3072, 8192, 12, 64)])
+@pytest.mark.parametrize("n,T,H,hd", [(14336, 4096, 32, 128), (28672, 2048, 64, 128), (3072, 8192, 12, 64),
+                                      (18944, 2048, 28, 128)])
 def test_syrk_other_baseline_shapes(ops, n, T, H, hd):
-    """Llama-3-8B (d_int 14336), Llama-2-70B (d_int 28672), OPT-125M (3072) operand widths."""
+    """Llama-3-8B (d_int 14336), Llama-2-70B (d_int 28672), OPT-125M (3072), Qwen2.5-7B (d_int 18944,
+    28 heads: d = 3584) operand widths."""
     x = activations(T, n, n)
     c = torch.zeros(n, n, device=DEV)
     ops.syrk_(c, x)

@@ -59,7 +59,14 @@ def compressed_ppl(adapter, tmp_path, layers, masks, tag):
     assert os.path.exists(os.path.join(out, f"{adapter.rebuild_module}.py"))
     model, _ = reload_compressed_model(out, device=DEV)
     assert type(model).__module__.endswith(adapter.rebuild_module)
-    return compute_perplexity(model, None, bs=4, dataset="synthetic", n_samples=8, seq_len=96)
+    ppl = compute_perplexity(model, None, bs=4, dataset="synthetic", n_samples=8, seq_len=96)
+    # perplexity of a random-init model barely depends on its weights; the logits do
+    from modegpt_b200.eval import HELD_OUT_SEED, synthetic_tokens
+
+    x = synthetic_tokens(4, 96, model.config.vocab_size, HELD_OUT_SEED).to(DEV)
+    with torch.no_grad():
+        logits = model(x, use_cache=False).logits.float().cpu().numpy()
+    return ppl, logits
 
 
 @pytest.mark.parametrize("tag", ["llama_mha", "llama_gqa", "qwen3_gqa"])
@@ -121,11 +128,14 @@ def test_pipeline_matches_reference(golden, tmp_path, tag):
         assert (v_a == v_r).double().mean() > 0.97 and (o_a == o_r).double().mean() > 0.97
 
     # perplexity of the rebuilt model: ours vs the reference's tensors through the same class
-    ppl_ours = compressed_ppl(adapter, tmp_path, ours, masks, "ours")
+    ppl_ours, logits_ours = compressed_ppl(adapter, tmp_path, ours, masks, "ours")
     adapter_ref = make_adapter(g, tmp_path)
-    ppl_ref = compressed_ppl(adapter_ref, tmp_path, ref_layers, ref_masks, "ref")
+    ppl_ref, logits_ref = compressed_ppl(adapter_ref, tmp_path, ref_layers, ref_masks, "ref")
     assert np.isfinite(ppl_ours) and np.isfinite(ppl_ref)
     assert abs(ppl_ours - ppl_ref) < 0.05, (ppl_ours, ppl_ref)
+    # the sensitive check: the two rebuilt models are the same FUNCTION (bf16 forward noise only;
+    # V/O sign flips cancel inside each head)
+    assert rel(logits_ours, logits_ref) < 2e-2, rel(logits_ours, logits_ref)
 
 
 @pytest.mark.parametrize("preset", ["tiny-llama", "tiny-llama-gqa", "tiny-qwen3", "tiny-qwen2", "tiny-opt"])
