@@ -24,8 +24,9 @@ memory, while 8 raw writer threads reach 26 GB/s on the same file system.
 Measured alternatives (Llama-2-7B, 10 GB of layer files): per-layer pinned staging buffers pin
 memory at ~1 GB/s and stall every other CUDA call meanwhile (+3 s on the calibration it overlapped);
 pageable `tensor.cpu()` from the saver threads slowed the kernel-launching threads 2.5x.  The
-bounce buffers cost 3 x 128 MB of pinned memory once.  `submit` blocks when `max_in_flight` jobs are
-pending, which bounds the device and host memory held by results waiting to be written.
+`submit` blocks when `max_in_flight` jobs are pending; host memory in flight is bounded by the pinned
+pool anyway (a job waits for its pool buffers before it is staged), so the limit is generous (64):
+at 16 the short Q/K stage of a 7B run spent 2.4 ms per layer waiting for slots.
 """
 from __future__ import annotations
 
@@ -41,7 +42,7 @@ _SLICE = 64 << 20
 
 
 class LayerWriter:
-    def __init__(self, n_threads: int = 8, max_in_flight: int = 16, device=None, n_stagers: int = 3,
+    def __init__(self, n_threads: int = 8, max_in_flight: int = 64, device=None, n_stagers: int = 3,
                  pool_buffer_bytes: int = 0, pool_bytes: int = 2 << 30):
         # pinned staging pool (CUDA only): `pool_buffer_bytes` = size of one buffer (0 = no pool)
         self._pool_free: list = []
