@@ -50,8 +50,39 @@ def run(files, workers, savers=8, stagers=3):
           + " ".join(f"{k}={v:.2f}" for k, v in t.items()), flush=True)
 
 
+def run_concurrent(vo_group):
+    """mlp (2 workers) on the calling thread; qk + vo on a second thread / stream."""
+    import threading
+    adapter = ModelAdapter.from_model(model, None)
+    adapter.config = CompressionConfig(model="x", order="mlp,qk,vo", nystrom_ridge=1e-4, ridge_vo=1e-5,
+                                       ridge_qk=1e-2, keep_layers_in_memory=True, mlp_workers=2, vo_group=vo_group)
+    err = []
+    side = torch.cuda.Stream()
+    def attn():
+        try:
+            torch.cuda.set_device(dev)
+            with torch.no_grad(), torch.cuda.stream(side):
+                compress_qk(adapter, (cov_q, cov_k), keep, target_layers=layers)
+                compress_vo(adapter, cov_x, keep, target_layers=layers)
+            side.synchronize()
+        except BaseException as e:
+            err.append(e)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    th = threading.Thread(target=attn); th.start()
+    compress_nystrom(adapter, cov_mlp, keep, layers)
+    t_mlp = time.perf_counter() - t0
+    th.join(); torch.cuda.synchronize()
+    total = 1e3 * (time.perf_counter() - t0) / L
+    assert not err, err
+    print(f"concurrent stages (vo_group={vo_group}): {total:6.2f} ms/layer  (mlp alone finished at {1e3 * t_mlp / L:.2f})", flush=True)
+    adapter._layer_store.clear()
+
+
 run(False, 2)
 run(False, 2)
+if os.environ.get("CONCURRENT"):
+    for g in (1, 2, 4, 1, 2):
+        run_concurrent(g)
 cfgs = os.environ.get("CFGS", "2,8,3;2,4,2;2,2,1;2,12,3;1,8,3;1,2,1")
 for cfg in cfgs.split(";"):
     run(True, *(int(v) for v in cfg.split(",")))
