@@ -293,6 +293,54 @@ def test_type1_concurrent_factorizations_are_timing_independent(ops):
             assert rel(down.float().cpu().numpy(), ref[2].float().cpu().numpy()) < 1e-3
 
 
+_POISON_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+from modegpt_b200 import ops
+g = torch.Generator().manual_seed(5)
+n, d, T, H, hd, r = 1160, 256, 4096, 4, 64, 48
+x = (torch.randn(T, n, generator=g) * torch.exp(0.7 * torch.randn(n, generator=g))).bfloat16().cuda()
+c = torch.zeros(n, n, device="cuda"); ops.syrk_(c, x); ops.finalize_sym_(c, 1.0 / T)
+wd = (torch.randn(d, n, generator=g) * 0.05).bfloat16().cuda()
+s = ops.ridge_scores(c, 1e-3); idx = ops.select_k(s, 870)
+down = ops.nystrom_down(c, idx, wd, refine=True)
+cx = c[:d, :d].contiguous()
+wv = (torch.randn(H * hd, d, generator=g) * 0.05).bfloat16().cuda()
+wo = (torch.randn(d, H * hd, generator=g) * 0.05).bfloat16().cuda()
+out = {"s": s.cpu(), "idx": idx.cpu(), "down": down.float().cpu()}
+for m in (0, 1):
+    v, o = ops.vo_compress(cx, 1e-5, wv, wo, H, H, hd, r, method=m, out_dtype=torch.float32)
+    out[f"v{m}"], out[f"o{m}"] = v.cpu(), o.cpu()
+v, o = ops.vo_compress(cx, 1e-5, wv[:2 * hd].contiguous(), wo, H, 2, hd, r, out_dtype=torch.float32)
+out["vg"], out["og"] = v.cpu(), o.cpu()
+torch.save(out, sys.argv[1])
+"""
+
+
+def test_workspaces_are_never_read_before_written(tmp_path):
+    """Every decomposition entry point with its caller-provided workspace poisoned (all bytes 0xFF:
+    NaN as bf16 / fp32 / fp64, -1 as int) must produce exactly what it produces on a fresh one —
+    a kernel that reads workspace it did not write would otherwise pass on zero-filled memory."""
+    import os
+    import subprocess
+    import sys
+
+    res = {}
+    for tag, env in (("clean", {}), ("poisoned", {"MG_POISON_WS": "1"})):
+        path = tmp_path / f"{tag}.pt"
+        r = subprocess.run([sys.executable, "-c", _POISON_CHILD, str(path)], env={**os.environ, **env},
+                           capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = torch.load(path)
+    for k, v in res["clean"].items():
+        w = res["poisoned"][k]
+        assert torch.isfinite(w.float()).all(), k
+        if k == "idx":
+            assert torch.equal(v, w)
+        else:
+            assert rel(w.float().numpy(), v.float().numpy()) < 1e-5, k
+
+
 def test_select_k_edge_cases(ops):
     s = torch.tensor([3.0, 1.0, 2.0, 1.0, 5.0, 1.0, -2.0, 0.0], device=DEV)
     assert ops.select_k(s, 3).tolist() == [1, 6, 7]                 # ties resolve to the lower index
