@@ -11,7 +11,12 @@ random-init weights (initialised on the CPU, then copied), same tokens.
   2. decompositions of every layer on the ORACLE's statistics: kept MLP rows, Q/K masks and biases
      must be identical; W_down / V' / O' within 1e-3 of the oracle's bf16-rounded tensors.
 
-    python tools/config1_opt125m.py [out.json]        (TEST TOOLING: imports oracle/)
+Runs as a GPU test (`pytest -m gpu`, ~75 s of which 60 s are the CPU oracle) and as a script:
+
+    python tests/test_gpu_config1_opt125m.py [out.json]
+
+The report goes to $MG_REPORT_DIR/config1_opt125m.json when that variable is set
+(profiles/r2_config1_opt125m.json is such a report).
 """
 import json
 import sys
@@ -32,8 +37,7 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def main():
-    out_path = sys.argv[1] if len(sys.argv) > 1 else None
+def run_config1() -> dict:
     from modegpt_b200.adapters.CompressionConfig import CompressionConfig
     from modegpt_b200.adapters.model_adapter import ModelAdapter
     from modegpt_b200.calibration import load_calibs
@@ -146,11 +150,40 @@ def main():
     res["all_index_sets_identical"] = all(p["mlp_rows_identical"] and p["qk_q_identical"] and p["qk_k_identical"]
                                           and p["qk_bias_identical"] for p in per_layer)
     res["worst_rel"] = {k: max(p[k] for p in per_layer) for k in ("mlp_down_rel", "vo_v_rel", "vo_o_rel")}
-    text = json.dumps(res, indent=1)
-    print(text)
-    if out_path:
-        Path(out_path).write_text(text)
+    return res
+
+
+try:
+    import pytest
+
+    @pytest.mark.gpu
+    def test_config1_opt125m_cpu_oracle_pipeline_vs_gpu():
+        import os
+
+        res = run_config1()
+        out = os.environ.get("MG_REPORT_DIR")
+        if out:
+            Path(out, "config1_opt125m.json").write_text(json.dumps(res, indent=1))
+        st = res["statistics_rel_vs_oracle"]
+        assert max(st.values()) < 3e-3, st           # bf16 GPU forward vs fp32 CPU forward
+        for p in res["layers"]:
+            assert p["qk_q_identical"] and p["qk_k_identical"] and p["qk_bias_identical"], p
+            assert p["vo_v_rel"] < 1e-3 and p["vo_o_rel"] < 1e-3 and p["vo_v_identical"] > 0.9, p
+            assert p["vo_o_bias_max_abs_diff"] < 1e-3, p
+            if p["mlp_rows_identical"]:
+                assert p["mlp_up_bias_identical"], p
+                assert p["mlp_down_rel"] < 1e-3 and p["mlp_down_identical"] > 0.95, p
+            else:
+                # a different selection is admissible only between candidates whose scores sit
+                # inside the fp32 error of the scores at the threshold (north_star's noise rule)
+                assert p["mlp_rows_differing"] <= 4, p
+                assert p["mlp_rows_max_rel_gap_to_threshold"] < 2.0 * p["mlp_scores_rel_err"] + 1e-5, p
+except ImportError:      # script use without pytest
+    pass
 
 
 if __name__ == "__main__":
-    main()
+    report = json.dumps(run_config1(), indent=1)
+    print(report)
+    if len(sys.argv) > 1:
+        Path(sys.argv[1]).write_text(report)
