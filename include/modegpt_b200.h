@@ -52,6 +52,13 @@ int mg_syrk_bf16_f32(const void* X, int64_t T, int64_t n, int64_t ldx, float* C,
 int mg_syrk_heads_bf16_f32(const void* X, int64_t T, int64_t n, int64_t ldx, int hd, float* C,
                            float alpha, int accumulate, void* stream);
 
+/* heads[h] += alpha * (diagonal hd x hd block h of the upper-triangular Gram `full` [n, n], mirrored
+ * to a full block).  With mg_syrk_bf16_f32 on the whole projection this gives the per-head Grams
+ * for head dims mg_syrk_heads_bf16_f32 does not take (e.g. OPT-2.7b's 80): H times the flops of
+ * the block-diagonal tile set on a matrix that is small anyway. */
+int mg_add_diag_blocks_f32(const float* full, int64_t n, int64_t ld, int hd, float alpha, float* heads,
+                           void* stream);
+
 /* acc[0] += sum_rows (1 - cos(x_in[row], x_out[row])), accumulated in fp64.
  * Replaces the Block-Influence loop body, src/calibration.py:118-124. */
 int mg_bi_cosine_bf16(const void* x_in, int64_t ld_in, const void* x_out, int64_t ld_out,

@@ -24,6 +24,7 @@ SIGNATURES: dict[str, tuple] = {
     "mg_error_string": (C.c_char_p, [i32]),
     "mg_syrk_bf16_f32": (i32, [vp, i64, i64, i64, vp, i64, f32, i32, vp]),
     "mg_syrk_heads_bf16_f32": (i32, [vp, i64, i64, i64, i32, vp, f32, i32, vp]),
+    "mg_add_diag_blocks_f32": (i32, [vp, i64, i64, i32, f32, vp, vp]),
     "mg_bi_cosine_bf16": (i32, [vp, i64, vp, i64, i64, i64, vp, vp]),
     "mg_finalize_sym_f32": (i32, [vp, i64, i64, f32, vp]),
     "mg_scale_f32": (i32, [vp, i64, f32, vp]),

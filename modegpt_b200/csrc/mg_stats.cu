@@ -132,6 +132,22 @@ __global__ void __launch_bounds__(256) pack_upper_kernel(float* __restrict__ C, 
   }
 }
 
+// heads[h][i][j] += alpha * full[h*hd + min(i,j)][h*hd + max(i,j)]: the diagonal hd x hd blocks of an
+// upper-triangular Gram, mirrored into full per-head blocks (head dims the block-diagonal tile set
+// of the engine does not cover: anything but 32 / 64 / 128)
+__global__ void __launch_bounds__(256) add_diag_blocks_kernel(const float* __restrict__ full, int64_t ld,
+                                                              int hd, float alpha,
+                                                              float* __restrict__ heads) {
+  const int h = blockIdx.x;
+  const float* blk = full + (static_cast<int64_t>(h) * hd) * ld + static_cast<int64_t>(h) * hd;
+  float* out = heads + static_cast<int64_t>(h) * hd * hd;
+  for (int e = threadIdx.x; e < hd * hd; e += blockDim.x) {
+    const int i = e / hd, j = e - i * hd;
+    const int r = i < j ? i : j, c = i < j ? j : i;
+    out[e] += alpha * blk[static_cast<int64_t>(r) * ld + c];
+  }
+}
+
 __global__ void scale_kernel(float* __restrict__ x, int64_t count, float scale) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
@@ -229,6 +245,16 @@ int mg_finalize_sym_f32(float* C, int64_t n, int64_t ldc, float scale, void* str
   const int nb = static_cast<int>((n + 31) / 32);
   finalize_sym_kernel<<<dim3(nb, nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(C, n, ldc,
                                                                                     scale);
+  return cuda_rc();
+}
+
+int mg_add_diag_blocks_f32(const float* full, int64_t n, int64_t ld, int hd, float alpha, float* heads,
+                           void* stream) {
+  if (!full || !heads) return -1;
+  if (n <= 0 || hd <= 0 || n % hd) return -2;
+  if (ld < n) return -7;
+  add_diag_blocks_kernel<<<static_cast<unsigned>(n / hd), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      full, ld, hd, alpha, heads);
   return cuda_rc();
 }
 

@@ -29,6 +29,8 @@ PRESETS = {
     "tiny-qwen3": ("qwen3", 256, 4, 2, 64, 512, 3, 512),
     "tiny-qwen2": ("qwen2", 256, 4, 2, 64, 512, 3, 512),
     "tiny-opt": ("opt", 256, 4, 4, 64, 512, 3, 512),
+    "tiny-llama-hd80": ("llama", 320, 4, 2, 80, 512, 3, 512),     # a head dim the 32/64/128 tile sets do not cover
+    "tiny-opt-hd80": ("opt", 320, 4, 4, 80, 512, 3, 512),         # OPT-2.7b's head dim
 }
 
 

@@ -43,6 +43,18 @@ def syrk_(C: torch.Tensor, X: torch.Tensor, alpha: float = 1.0, accumulate: bool
                                int(accumulate), _stream()))
 
 
+_SCRATCH: dict = {}
+
+
+def _scratch_square(n: int, device) -> torch.Tensor:
+    """One reusable [n, n] fp32 scratch per (device, n, stream): stream-ordered reuse is safe."""
+    key = (str(device), n, torch.cuda.current_stream(device).cuda_stream)
+    buf = _SCRATCH.get(key)
+    if buf is None:
+        buf = _SCRATCH[key] = torch.empty(n, n, dtype=torch.float32, device=device)
+    return buf
+
+
 def syrk_heads_(C: torch.Tensor, X: torch.Tensor, alpha: float = 1.0,
                 accumulate: bool = True) -> None:
     """C[H,hd,hd] (+)= alpha * per-head Gram of X[T, H*hd] (bf16)."""
@@ -55,9 +67,19 @@ def syrk_heads_(C: torch.Tensor, X: torch.Tensor, alpha: float = 1.0,
     H, hd = C.shape[0], C.shape[1]
     if H * hd != n:
         raise ValueError(f"syrk_heads_: X has {n} columns, C describes {H}x{hd}")
-    check("mg_syrk_heads_bf16_f32",
-          lib.mg_syrk_heads_bf16_f32(X.data_ptr(), T, n, ldx, hd, C.data_ptr(), alpha,
-                                     int(accumulate), _stream()))
+    if hd in (32, 64, 128):
+        check("mg_syrk_heads_bf16_f32",
+              lib.mg_syrk_heads_bf16_f32(X.data_ptr(), T, n, ldx, hd, C.data_ptr(), alpha,
+                                         int(accumulate), _stream()))
+        return
+    # other head dims (OPT-2.7b: 80, 96, ...): Gram of the whole projection, then its diagonal blocks
+    full = _scratch_square(n, X.device)
+    check("mg_syrk_bf16_f32",
+          lib.mg_syrk_bf16_f32(X.data_ptr(), T, n, ldx, full.data_ptr(), full.stride(0), 1.0, 0, _stream()))
+    if not accumulate:
+        C.zero_()
+    check("mg_add_diag_blocks_f32",
+          lib.mg_add_diag_blocks_f32(full.data_ptr(), n, full.stride(0), hd, alpha, C.data_ptr(), _stream()))
 
 
 def bi_cosine_(acc: torch.Tensor, x_in: torch.Tensor, x_out: torch.Tensor) -> None:

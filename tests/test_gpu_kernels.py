@@ -48,6 +48,20 @@ def test_syrk_matches_oracle(ops, T, n):
     assert rel(upper(c.cpu().numpy()), upper(ref)) < 1e-3
 
 
+@pytest.mark.parametrize("H,hd", [(4, 80), (3, 96), (5, 40)])
+def test_syrk_heads_other_head_dims(ops, H, hd):
+    """Head dims outside {32, 64, 128} (OPT-2.7b: 80): Gram of the whole projection + its diagonal
+    blocks; accumulate and overwrite modes."""
+    x, y = shaped(700, H * hd, seed=hd).to(DEV), shaped(300, H * hd, seed=hd + 1).to(DEV)
+    c = torch.zeros(H, hd, hd, device=DEV)
+    ops.syrk_heads_(c, x)
+    ops.syrk_heads_(c, y, alpha=0.5)
+    ref = O.gram_heads(x.float().cpu().numpy(), H, hd) + 0.5 * O.gram_heads(y.float().cpu().numpy(), H, hd)
+    assert rel(c.cpu().numpy(), ref) < 1e-5
+    ops.syrk_heads_(c, y, accumulate=False)
+    assert rel(c.cpu().numpy(), O.gram_heads(y.float().cpu().numpy(), H, hd)) < 1e-5
+
+
 def test_syrk_accumulates_and_overwrites(ops):
     x, y = shaped(500, 384, 1).to(DEV), shaped(260, 384, 2).to(DEV)
     c = torch.zeros(384, 384, device=DEV)
@@ -337,8 +351,15 @@ def test_workspaces_are_never_read_before_written(tmp_path):
         assert torch.isfinite(w.float()).all(), k
         if k == "idx":
             assert torch.equal(v, w)
+        elif k == "down":    # bf16-rounded: isolated one-ulp flips from the order of split-K sums
+            assert (v == w).float().mean() > 0.99 and rel(w.numpy(), v.numpy()) < 1e-3
+        elif k == "s":
+            assert rel(w.numpy(), v.numpy()) < 1e-5
         else:
-            assert rel(w.float().numpy(), v.float().numpy()) < 1e-5, k
+            # the two processes' statistics differ in their last bits (split-K order in the SYRK);
+            # eigenvectors amplify that by 1 / gap and may flip sign: compare magnitudes at 1e-3 —
+            # a poisoned read would give NaNs or O(1) differences
+            assert rel(w.abs().numpy(), v.abs().numpy()) < 1e-3, k
 
 
 def test_select_k_edge_cases(ops):

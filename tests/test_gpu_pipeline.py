@@ -138,7 +138,8 @@ def test_pipeline_matches_reference(golden, tmp_path, tag):
     assert rel(logits_ours, logits_ref) < 2e-2, rel(logits_ours, logits_ref)
 
 
-@pytest.mark.parametrize("preset", ["tiny-llama", "tiny-llama-gqa", "tiny-qwen3", "tiny-qwen2", "tiny-opt"])
+@pytest.mark.parametrize("preset", ["tiny-llama", "tiny-llama-gqa", "tiny-qwen3", "tiny-qwen2", "tiny-opt",
+                                    "tiny-llama-hd80", "tiny-opt-hd80"])
 def test_cli_flow_on_synthetic_presets(tmp_path, preset, monkeypatch):
     """`run_modegpt.main` end to end: files on disk, reload through auto_map, finite perplexity."""
     from modegpt_b200.adapters.CompressionConfig import CompressionConfig
