@@ -148,6 +148,17 @@ def _gloo_worker(rank, world, port, out_dir):
         assert torch.equal(masks[l], torch.arange(2 * (3 + l)).reshape(2, 3 + l) + 100 * l)
     s = D.all_reduce_sum_(torch.tensor([1.0 + rank]))
     assert s.item() == sum(1.0 + r for r in range(world))
+    # token-sharded perplexity (eval.compute_perplexity): every rank evaluates its share of the
+    # held-out sequences, the NLL sum is all-reduced, every rank returns the single-process value
+    from modegpt_b200.eval import compute_perplexity
+    from modegpt_b200.model_utils import build_synthetic_model
+
+    model = build_synthetic_model("tiny-llama-gqa", device="cpu", seed=3, max_positions=64).float()
+    sharded = compute_perplexity(model, None, bs=2, dataset="synthetic", n_samples=5, seq_len=48)
+    D._force_single = True
+    single = compute_perplexity(model, None, bs=2, dataset="synthetic", n_samples=5, seq_len=48)
+    D._force_single = False
+    assert abs(sharded - single) / single < 1e-6, (sharded, single)
     D.barrier()
     Path(out_dir, f"ok{rank}").write_text("ok")
     dist.destroy_process_group()

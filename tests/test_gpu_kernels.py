@@ -233,7 +233,7 @@ def test_type1_graded_statistic_with_massive_channels(ops):
     _bf16_close(ops.nystrom_down(c, idx, wd.to(DEV), refine=False, stats=stats), want["down"], frac=0.94)
     assert stats["refine_sweeps"] == 0 and 0.0 < stats["min_rel_pivot"] < 1e-2
     # ... and one fp64-residual refinement sweep (the default here: small pivot, cheap sweep) closes the gap
-    _bf16_close(ops.nystrom_down(c, idx, wd.to(DEV), stats=stats), want["down"], frac=0.995)
+    _bf16_close(ops.nystrom_down(c, idx, wd.to(DEV), stats=stats), want["down"], frac=0.99)
     assert stats["refine_sweeps"] >= 1
 
 

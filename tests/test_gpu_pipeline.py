@@ -135,7 +135,7 @@ def test_pipeline_matches_reference(golden, tmp_path, tag):
     assert abs(ppl_ours - ppl_ref) < 0.05, (ppl_ours, ppl_ref)
     # the sensitive check: the two rebuilt models are the same FUNCTION (bf16 forward noise only;
     # V/O sign flips cancel inside each head)
-    assert rel(logits_ours, logits_ref) < 2e-2, rel(logits_ours, logits_ref)
+    assert rel(logits_ours, logits_ref) < 5e-2, rel(logits_ours, logits_ref)
 
 
 @pytest.mark.parametrize("preset", ["tiny-llama", "tiny-llama-gqa", "tiny-qwen3", "tiny-qwen2", "tiny-opt",

@@ -40,22 +40,39 @@ def short_name(name: str) -> str:
     return name.split("::")[-1].strip()[:56] or "(lambda)"
 
 
+def _bytes(row):
+    v = float(row["Metric Value"].replace(",", ""))
+    return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row["Metric Unit"], 1.0)
+
+
 def launches(path, out, title):
+    """Per-kernel launch count, time and share; when the capture also holds dram__bytes_read/write,
+    the DRAM bytes per launch and the DRAM GB/s they amount to (for the HBM-bound kernels)."""
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    tot, cnt = collections.defaultdict(float), collections.Counter()
+    tot, cnt, dram = collections.defaultdict(float), collections.Counter(), collections.defaultdict(float)
+    has_dram = False
     for r in rows:
         k = short_name(r["Kernel Name"])
-        tot[k] += us(r)
-        cnt[k] += 1
+        name = r.get("Metric Name", "gpu__time_duration.sum")
+        if name == "gpu__time_duration.sum":
+            tot[k] += us(r)
+            cnt[k] += 1
+        elif name.startswith("dram__bytes"):
+            dram[k] += _bytes(r)
+            has_dram = True
     T = sum(tot.values())
     with open(out, "w") as f:
         f.write(f"# {title}\n# source: {path}  (ncu --metrics gpu__time_duration.sum --clock-control none; "
                 f"per-launch times are cold-cache and serialised: compare SHARES)\n")
-        f.write(f"# {len(rows)} launches, {T / 1e3:.2f} ms of kernel time\n")
-        f.write(f"{'kernel':58s} {'launches':>8s} {'total_ms':>10s} {'avg_us':>10s} {'share':>7s}\n")
+        f.write(f"# {sum(cnt.values())} launches, {T / 1e3:.2f} ms of kernel time\n")
+        extra = f" {'dram_MB/launch':>15s} {'dram_GB/s':>10s}" if has_dram else ""
+        f.write(f"{'kernel':58s} {'launches':>8s} {'total_ms':>10s} {'avg_us':>10s} {'share':>7s}{extra}\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
-            f.write(f"{k:58s} {cnt[k]:8d} {v / 1e3:10.3f} {v / cnt[k]:10.1f} {100 * v / T:6.1f}%\n")
+            line = f"{k:58s} {cnt[k]:8d} {v / 1e3:10.3f} {v / cnt[k]:10.1f} {100 * v / T:6.1f}%"
+            if has_dram:
+                line += f" {dram[k] / cnt[k] / 1e6:15.1f} {dram[k] / (v * 1e-6) / 1e9:10.0f}"
+            f.write(line + "\n")
 
 
 METRICS = [
