@@ -5,8 +5,10 @@
 #include "mg_linalg.cuh"
 
 #include <atomic>
+#include <cstdint>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -36,13 +38,25 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16
   lo = __float2bfloat16_rn(r2);
 }
 
-// 1/sqrt(x) for x in the float range: single-precision seed y0 (relative error e ~ 2^-22) and one
-// third-order correction y0 (1 + e/2 + 3 e^2 / 8), e = 1 - x y0^2 — the neglected term is
-// 5 e^3 / 16 < 1e-19.  Four dependent fp64 operations; the pivot loops sit on this latency.
-__device__ __forceinline__ double rsqrt_pos(double x) {
-  const double y0 = static_cast<double>(rsqrtf(static_cast<float>(x)));
-  const double e = fma(-x * y0, y0, 1.0);
-  return fma(y0 * e, fma(0.375, e, 0.5), y0);
+// 1/sqrt(x): the 64-bit MUFU seed (computed from the upper word, relative error e below 2^-17)
+// and one second-order correction y0 (1 + e/2), e = 1 - x y0^2.  The neglected term 3 e^2 / 8 is
+// below 3e-11 — the panels are stored in fp32 (6e-8) — and the chain is MUFU + three dependent fp64
+// operations with no float conversions; the pivot loops sit on this latency.  Non-positive or
+// non-finite x gives NaN / inf, which the caller detects after the loop.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double h = 0.5 * y0;
+  const double e = fma(-(x * y0), y0, 1.0);
+  return fma(h, e, y0);
+}
+
+// named barriers (ids 1..15; 0 is __syncthreads): `count` threads in total arrive or wait
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // D (8 x 8, fp64) += A (8 x 4, row) * B (4 x 8, col) on the FP64 tensor cores; per-thread fragments:
@@ -117,71 +131,145 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 // potrf128: Cholesky of one 128 x 128 diagonal block, fp64, one CTA of 512 threads.
 // Four 32-wide sub-panels; per sub-panel
 //   (1) warp 0 factors the 32 x 32 diagonal block entirely in registers (lane k owns column k,
-//       pivot row broadcast by shuffles),
-//   (2) one thread per remaining column does the 32-step forward substitution,
-//   (3) all threads apply the rank-32 update to the trailing part of the block.
+//       pivot row broadcast by shuffles) and leaves a pre-scaled copy U'[m][i] = U[m][i] / U[i][i],
+//   (2) one thread per remaining column does the 32-step forward substitution (one fused
+//       multiply-add per step on the chain, thanks to U'),
+//   (3) the rank-32 update of the trailing part of the block on the FP64 tensor cores.
+// The kernel sits on the critical path of every blocked factorisation, so the sub-panels are
+// software-pipelined around warp 0: it solves the 32 columns of the NEXT diagonal block alone,
+// updates that block together with warps 1..3 and goes straight on to (1) of the next sub-panel;
+// the other fifteen warps solve the remaining columns, apply the rest of the update and write
+// finished rows out behind it.  Chain per sub-panel: (1) + (2) of one warp + ten 8 x 8 tiles on
+// four warps (tools/gpu_probe_clocks.py prints the stamps; tools/ubench_fp64*.cu the instruction
+// latencies and rates the layout follows from).
+// Named barriers: 4 = "(2) done by warp 0" and 1 = "(2) done by everyone" (warp 0 only arrives),
+// 3 = "next diagonal block updated" (warps 1..3 arrive, warp 0 waits).
 // ---------------------------------------------------------------------------------------------
-constexpr int kDiagLd = kNB + 2;   // even: rows stay 16-byte aligned for double2 accesses
+constexpr int kDiagLd = kNB + 4;   // even: rows stay 16-byte aligned for double2 accesses; 4 rows x
+                                   // 4 consecutive doubles (an mma fragment per half-warp) hit 16 banks
 constexpr int kPotrfThreads = 512;
-constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 128);
+// a[128][132] | invd[2][32] | urow[2][32] | uscaled[2][32][32]
+constexpr size_t kPotrfSmem = sizeof(double) * (kNB * kDiagLd + 128 + 2 * 32 * 32);
 
 __global__ void __launch_bounds__(kPotrfThreads, 1)
     potrf128_kernel(float* __restrict__ A, int64_t ld, int64_t j0, int nb,
                     float* __restrict__ t_fwd, float* __restrict__ t_bwd, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
-  double* a = sm;                     // [128][130], upper triangle live
-  double* invd = sm + kNB * kDiagLd;  // [32] reciprocal pivots of the current sub-panel, + [2][32] pivot row
+  double* a = sm;                     // [128][132], upper triangle live
+  double* invd = sm + kNB * kDiagLd;  // [2][32] reciprocal pivots, by sub-panel parity
+  double* urow = invd + 64;           // [2][32] pivot row exchange of warp 0 (16-byte aligned)
+  double* usc = invd + 128;           // [2][32][32] pre-scaled diagonal blocks, by sub-panel parity
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
+  const int fm = lane & 3, fr = lane >> 2;   // mma.m8n8k4 fragment coordinates
 
-  for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
-    const int i = e >> 7, k = e & 127;
-    double v = (i == k) ? 1.0 : 0.0;  // identity padding for a short last block
-    if (i < nb && k < nb && i <= k) v = static_cast<double>(A[(j0 + i) * ld + (j0 + k)]);
-    a[i * kDiagLd + k] = v;
+  MG_CLK(21);
+  // All loads of a thread are in flight at once: under the bulk GEMMs of the other lanes a round
+  // trip to L2 / HBM costs a microsecond, and this kernel is the head of the chain.  A full block
+  // with 16-byte aligned rows is read as eight 16-byte loads per thread (the lower triangle comes
+  // along and is dropped); anything else — the short last block, odd leading dimensions — as 32
+  // predicated scalar loads.
+  if (nb == kNB && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+    constexpr int kPer = kNB * kNB / 4 / kPotrfThreads;   // 8
+    float4 v[kPer];
+    const int k = 4 * (t & 31), i0 = t >> 5;              // rows i0, i0 + 16, ...
+    const float* src = A + (j0 + i0) * ld + j0 + k;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) v[q] = *reinterpret_cast<const float4*>(src + q * 16 * ld);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = i0 + 16 * q;
+      double* dst = a + i * kDiagLd + k;
+      *reinterpret_cast<double2*>(dst) =
+          make_double2(i <= k ? static_cast<double>(v[q].x) : 0.0, i <= k + 1 ? static_cast<double>(v[q].y) : 0.0);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2(i <= k + 2 ? static_cast<double>(v[q].z) : 0.0,
+                                                          i <= k + 3 ? static_cast<double>(v[q].w) : 0.0);
+    }
+  } else {
+    constexpr int kPer = kNB * kNB / kPotrfThreads;
+    float v[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int e = t + q * kPotrfThreads, i = e >> 7, k = e & 127;
+      v[q] = (i == k) ? 1.f : 0.f;    // identity padding for a short last block
+      if (i < nb && k < nb && i <= k) v[q] = A[(j0 + i) * ld + (j0 + k)];
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int e = t + q * kPotrfThreads;
+      a[(e >> 7) * kDiagLd + (e & 127)] = static_cast<double>(v[q]);
+    }
   }
   MG_CLK(0);
   __syncthreads();
   MG_CLK(1);
 
+  // Outputs for rows [r0, r1) of U by `nth` threads (`tid` = 0..nth-1): the fp32 factor back into A,
+  //   forward block   T[m][i] = U[m][i], identity beyond nb;
+  //   backward block  T'[m'][i'] = U[nb-1-i'][nb-1-m'] for m' <= i' < nb, identity beyond: row r of
+  //                   U is column nb-1-r of T' (a padding row r >= nb is column r of the identity).
+  auto write_rows = [&](int r0, int r1, int tid, int nth) {
+    for (int e = tid; e < (r1 - r0) * kNB; e += nth) {
+      const int i = r0 + (e >> 7), k = e & 127;
+      const bool in = i < nb && k < nb;
+      const float x = (in && i <= k) ? static_cast<float>(a[i * kDiagLd + k]) : 0.f;
+      if (in && i <= k) A[(j0 + i) * ld + (j0 + k)] = x;
+      t_fwd[i * kTLd + k] = in ? x : (i == k ? 1.f : 0.f);
+    }
+    if (t_bwd == nullptr) return;
+    const int nr = r1 - r0;          // a multiple of 32: consecutive threads -> consecutive columns
+    for (int e = tid; e < nr * kNB; e += nth) {
+      const int mp = e / nr, r = r0 + (e - mp * nr);
+      float x;
+      int ip;
+      if (r < nb) {
+        ip = nb - 1 - r;
+        x = (mp <= ip) ? static_cast<float>(a[r * kDiagLd + (nb - 1 - mp)]) : 0.f;
+      } else {
+        ip = r;
+        x = (mp == ip) ? 1.f : 0.f;
+      }
+      t_bwd[mp * kTLd + ip] = x;
+    }
+  };
+
   const int nsub = (nb + 31) / 32;
   for (int kb = 0; kb < nsub; ++kb) {
     const int c0 = kb * 32;
+    double* inv_s = invd + (kb & 1) * 32;
+    double* us = usc + (kb & 1) * 1024;
     // (1) 32 x 32 diagonal block, one warp, lane k owns COLUMN k in registers (rows 0..k).
     //     Step j: lane j's reciprocal pivot is broadcast by shuffle, every lane scales its own
     //     entry of pivot row j (u_jk), folds it into its own diagonal and starts the rsqrt of that
     //     diagonal at once — lane j+1's is the next pivot, so the long-latency rsqrt overlaps the
     //     off-diagonal updates below — then the pivot row is exchanged through a double-buffered
-    //     32-entry shared array (one parallel store, broadcast loads).
+    //     32-entry shared array (one parallel store, broadcast loads).  Nothing on the chain looks
+    //     at the sign of a pivot: a non-positive one turns into NaNs, found after the loop.
     if (warp == 0) {
-      double* urow = invd + 32;          // [2][32] pivot row exchange (16-byte aligned)
       double col[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) col[i] = a[(c0 + i) * kDiagLd + c0 + lane];   // rows > lane: don't-care
       double diag = col[0];
 #pragma unroll
       for (int i = 1; i < 32; ++i) diag = (i == lane) ? col[i] : diag;
-      double inv_own = rsqrt_pos(diag);
+      double inv_own = rsqrt_fast(diag);
+      double inv_mine = 1.0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (lane == j && !(diag >= 1e-30 && diag <= 1e30)) {   // rare: non-positive (reported) / out of float range
-          if (!(diag > 0.0)) {
-            if (c0 + j < nb) atomicCAS(info, 0, static_cast<int>(j0 + c0 + j + 1));
-            diag = 1e-30;
-          }
-          inv_own = rsqrt(diag);
-        }
         const double inv = __shfl_sync(0xffffffffu, inv_own, j);
         // u_jk: own entry of pivot row j (lane j: the diagonal sqrt(d_j); lanes < j: unused)
         const double u = (lane == j ? diag : col[j]) * inv;
-        diag = (lane > j) ? fma(-u, u, diag) : diag;
-        if (lane == j) invd[j] = inv;
+        diag = fma(-u, u, diag);         // lanes <= j: dead value from here on
+        if (lane == j) {
+          inv_s[j] = inv;
+          inv_mine = inv;
+        }
         double* ur = urow + (j & 1) * 32;
         ur[lane] = u;
         __syncwarp();
         // lane j+1's value is the next pivot's: issued here so that its dependent chain interleaves
         // with the (independent) row updates below
-        inv_own = rsqrt_pos(diag);
+        inv_own = rsqrt_fast(diag);
         // rows j+1 .. 31 of the own column; entries at or below the own diagonal are don't-care,
         // so the pivot row is loaded and applied without predicates (batched 16-byte loads)
 #pragma unroll
@@ -192,27 +280,49 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
         }
         col[j] = u;                      // U[j][k]
       }
+      // a pivot that was not a positive finite number poisons every later one (NaN / inf), so the
+      // last diagonal entry tells whether the whole sub-panel is good
+      const double ulast = __shfl_sync(0xffffffffu, col[31], 31);
+      if (!(ulast > 0.0 && ulast < 1e150)) {
+        // rare: report the first bad pivot; the sub-panel becomes the identity so that everything
+        // downstream stays finite (the caller raises on `info`)
+        double ujj = col[0];
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+        for (int i = 1; i < 32; ++i) ujj = (i == lane) ? col[i] : ujj;
+        const unsigned bad = __ballot_sync(0xffffffffu, !(ujj > 0.0 && ujj < 1e150));
+        const int first = __ffs(bad) - 1;
+        if (lane == 0 && c0 + first < nb) atomicCAS(info, 0, static_cast<int>(j0 + c0 + first + 1));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) col[i] = (i == lane) ? 1.0 : 0.0;
+        inv_mine = 1.0;
+        inv_s[lane] = 1.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
         if (i <= lane) a[(c0 + i) * kDiagLd + c0 + lane] = col[i];
+        us[i * 32 + lane] = col[i] * inv_mine;   // U'[i][k]; rows > k are never read
+      }
     }
-    __syncthreads();
+    __syncthreads();   // (1) of this sub-panel visible; the other warps' update of the previous one done
     MG_CLK(2 + 3 * kb);
-    // (2) block row: forward substitution, one thread per column with the 32 rows in registers.
-    //     The triangular coefficients U[c0+i][c0+l] are the same for every column (broadcast
-    //     16-byte loads, independent of the running solution), so per column the chain is just
-    //     32 x (multiply, fused multiply-add); no shuffles, no intermediate barrier.
+    // (2) block row: forward substitution, one thread per column with the 32 rows in registers:
+    //     x_i = b_i / u_ii - sum_{m < i} U'[m][i] x_m.  The coefficients are the same for every
+    //     column (broadcast 16-byte loads, independent of the running solution), so per column the
+    //     chain is 32 fused multiply-adds; no shuffles, no intermediate barrier.  The phase is bound
+    //     by shared-memory bandwidth (256 16-byte loads per warp), so warp 0 — whose 32 columns are
+    //     the next diagonal block — runs it alone and the other warps follow behind barrier 4.
     const int rest = kNB - c0 - 32;  // columns right of the sub-panel (padding included)
-    if (t < rest) {
+    if (rest == 0) break;            // last sub-panel of a full block
+    auto solve_columns = [&]() {
+      if (t >= rest) return;
       const int k = c0 + 32 + t;
       double r[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = a[(c0 + i) * kDiagLd + k];
+      for (int i = 0; i < 32; ++i) r[i] = a[(c0 + i) * kDiagLd + k] * inv_s[i];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const double x = r[i] * invd[i];
-        r[i] = x;
-        const double* trow = a + (c0 + i) * kDiagLd + c0;
+        const double x = r[i];
+        const double* trow = us + i * 32;
 #pragma unroll
         for (int l2 = (i + 1) / 2; l2 < 16; ++l2) {
           const double2 tv = *reinterpret_cast<const double2*>(trow + 2 * l2);
@@ -222,56 +332,68 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[(c0 + i) * kDiagLd + k] = r[i];
-    }
-    __syncthreads();
-    MG_CLK(3 + 3 * kb);
-    // (3) rank-32 update of the trailing upper triangle on the FP64 tensor cores: 8 x 8 tiles of
-    //     A22 -= U12^T U12, eight mma.m8n8k4 per tile, tiles on or above the diagonal dealt to the
-    //     16 warps.  Fragment coordinates: A[i][m] and B[m][k] are both read from row c0+m of the
+    };
+    // (3) rank-32 update of the trailing upper triangle on the FP64 tensor cores, A22 -= U12^T U12 in
+    //     8 x 8 tiles, eight mma.m8n8k4 per tile (the only fp64 shape sm_100a has; 64 FMA/clk/SM,
+    //     the rate of the FMA pipe, for a quarter of its shared-memory traffic).  A warp takes one
+    //     tile row: tiles (ti, tk0 .. tk0+cnt-1), the A fragment shared by up to MAXC accumulation
+    //     chains.  Fragment coordinates: A[i][m] and B[m][k] are both read from row c0+m of the
     //     block (thread: m = lane & 3, i or k = lane >> 2); C rows lane >> 2, columns 2 (lane & 3).
-    {
-      const int nt = rest / 8;       // rest is a multiple of 32
-      const int fm = lane & 3, fr = lane >> 2;
-      for (int e = warp; e < nt * (nt + 1) / 2; e += kPotrfThreads / 32) {
-        int tk = static_cast<int>((sqrtf(8.f * static_cast<float>(e) + 1.f) - 1.f) * 0.5f);
-        while (tk * (tk + 1) / 2 > e) --tk;
-        while ((tk + 1) * (tk + 2) / 2 <= e) ++tk;
-        const int ti = e - tk * (tk + 1) / 2;
-        const int i0 = c0 + 32 + 8 * ti, k0 = c0 + 32 + 8 * tk;
-        double acc0 = 0.0, acc1 = 0.0;
+    auto tile_row = [&](auto maxc, int ti, int tk0, int cnt) {
+      constexpr int MAXC = decltype(maxc)::value;
+      double acc[MAXC][2];
 #pragma unroll
-        for (int m0 = 0; m0 < 32; m0 += 4) {
-          const double av = a[(c0 + m0 + fm) * kDiagLd + i0 + fr];
-          const double bv = a[(c0 + m0 + fm) * kDiagLd + k0 + fr];
-          dmma_m8n8k4(acc0, acc1, av, bv);
-        }
-        const int row = i0 + fr, colb = k0 + 2 * fm;
-        if (row <= colb) a[row * kDiagLd + colb] -= acc0;
-        if (row <= colb + 1) a[row * kDiagLd + colb + 1] -= acc1;
+      for (int q = 0; q < MAXC; ++q) acc[q][0] = acc[q][1] = 0.0;
+      const double* frag = a + (c0 + fm) * kDiagLd + c0 + 32 + fr;
+#pragma unroll
+      for (int m0 = 0; m0 < 32; m0 += 4) {
+        const double* row = frag + m0 * kDiagLd;
+        const double av = row[8 * ti];
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q)
+          if (q < cnt) dmma_m8n8k4(acc[q][0], acc[q][1], av, row[8 * (tk0 + q)]);
       }
+      const int r = c0 + 32 + 8 * ti + fr;
+#pragma unroll
+      for (int q = 0; q < MAXC; ++q) {
+        const int colb = c0 + 32 + 8 * (tk0 + q) + 2 * fm;
+        if (q < cnt && r <= colb) a[r * kDiagLd + colb] -= acc[q][0];
+        if (q < cnt && r <= colb + 1) a[r * kDiagLd + colb + 1] -= acc[q][1];
+      }
+    };
+    const int nt = rest / 8;         // 12, 8 or 4 tile rows; the first 4 are the next diagonal block
+    if (warp == 0) {
+      solve_columns();
+      __syncwarp();
+      named_arrive(4, kPotrfThreads);   // "the next diagonal block's columns are solved"
+      named_arrive(1, kPotrfThreads);
+      MG_CLK(3 + 3 * kb);
+      tile_row(std::integral_constant<int, 4>{}, 3, 3, 1);
+      named_sync(3, 128);
+      MG_CLK(4 + 3 * kb);
+      continue;                      // on to (1) of the next sub-panel
     }
-    __syncthreads();
-    MG_CLK(4 + 3 * kb);
+    named_sync(4, kPotrfThreads);
+    if (warp < 4) {                  // the other three tile rows of the next diagonal block
+      tile_row(std::integral_constant<int, 4>{}, warp - 1, warp - 1, 5 - warp);
+      named_arrive(3, 128);
+    }
+    solve_columns();
+    named_sync(1, kPotrfThreads);    // every column of the block row is solved
+    if (warp <= nt && nt > 4) {      // tile row warp-1, the tiles right of the next diagonal block
+      const int ti = warp - 1, tk0 = ti > 4 ? ti : 4;
+      tile_row(std::integral_constant<int, 8>{}, ti, tk0, nt - tk0);
+    }
+    // rows that are final and not yet written go out behind warp 0's next diagonal block; the
+    // longest update (first sub-panel) leaves no room for it, the last one has room for two
+    if (kb == 1) write_rows(0, 32, t - 32, kPotrfThreads - 32);
+    if (kb == 2) write_rows(32, 96, t - 32, kPotrfThreads - 32);
   }
+  __syncthreads();
 
-  // ---- outputs
-  for (int e = t; e < kNB * kNB; e += kPotrfThreads) {
-    const int i = e >> 7, k = e & 127;
-    const bool in = i < nb && k < nb;
-    const float x = (in && i <= k) ? static_cast<float>(a[i * kDiagLd + k]) : 0.f;
-    if (in && i <= k) A[(j0 + i) * ld + (j0 + k)] = x;
-    // forward block: T[m][i] = U[m][i]; identity beyond nb
-    t_fwd[i * kTLd + k] = in ? x : (i == k ? 1.f : 0.f);
-  }
+  // ---- the rows not written inside the loop (the last sub-panel; padding rows of a short block)
   MG_CLK(19);
-  // backward block: T'[m'][i'] = U[nb-1-i'][nb-1-m'] for m' <= i' < nb; identity beyond
-  for (int e = t; t_bwd != nullptr && e < kNB * kNB; e += kPotrfThreads) {
-    const int mp = e >> 7, ip = e & 127;
-    float x = (mp == ip) ? 1.f : 0.f;
-    if (mp < nb && ip < nb)
-      x = (mp <= ip) ? static_cast<float>(a[(nb - 1 - ip) * kDiagLd + (nb - 1 - mp)]) : 0.f;
-    t_bwd[mp * kTLd + ip] = x;
-  }
+  write_rows(nsub >= 3 ? 96 : (nsub == 2 ? 32 : 0), kNB, t, kPotrfThreads);
   MG_CLK(20);
 }
 
@@ -286,17 +408,23 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
 constexpr int kTrsmLanes = 8;                       // lanes sharing one column pair
 constexpr int kTrsmRows = 32 / kTrsmLanes;          // chunk rows owned by a lane (4)
 constexpr int kTrsmCpl = 2;                         // columns per lane: every T load feeds 8 FMAs
-constexpr int kTrsmThreads = 256;
-constexpr int kTrsmCols = kTrsmThreads / kTrsmLanes * kTrsmCpl;  // 64 columns per block
 constexpr int kXsLd = kNB + 4;                      // xs row stride (floats), 16-byte aligned rows
-constexpr size_t kTrsmSmem = sizeof(float) * (kTBlock + kTrsmCols * kXsLd + kNB) + 16;
+// THREADS per CTA = 128 (32 columns) or 256 (64 columns).  The substitution is bound by instruction
+// issue per scheduler, so 4-warp CTAs (one warp per scheduler, twice as many SMs for the same
+// columns) halve the time of the short launches on the panel chain; long launches are indifferent.
+constexpr int trsm_cols(int threads) { return threads / kTrsmLanes * kTrsmCpl; }
+constexpr size_t trsm_smem(int threads) {
+  return sizeof(float) * (kTBlock + trsm_cols(threads) * kXsLd + kNB) + 16;
+}
 
+template <int kTrsmThreads>
 __global__ void __launch_bounds__(kTrsmThreads, 2)
     trsm128_kernel(const float* __restrict__ tblock, int reversed, int nb,
                    const float* __restrict__ B, int64_t ldb, int64_t ncols, float alpha,
                    float* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ planes,
                    int64_t ldp, int64_t pstride, __nv_bfloat16* __restrict__ tplanes,
                    int64_t ldtp, int64_t tpstride, float* __restrict__ colsumsq) {
+  constexpr int kTrsmCols = trsm_cols(kTrsmThreads);
   extern __shared__ __align__(16) float smf[];
   float* T = smf;                          // [128][132]
   float* xs = smf + kTBlock;               // [64 cols][132]: xs[col][row]
@@ -342,7 +470,12 @@ __global__ void __launch_bounds__(kTrsmThreads, 2)
   MG_CLK(32);
   __syncthreads();                         // barrier initialised before anyone polls it
   mbar_wait(tbar, 0);
-  if (tid < kNB) invd[tid] = 1.f / T[tid * kTLd + tid];
+  if (tid < kNB) {
+    invd[tid] = 1.f / T[tid * kTLd + tid];
+    // with a zero diagonal, T[i][ip] vanishes for every ip <= i: the substitution below can apply
+    // row i of T to all rows a lane owns without selecting the ones still unsolved
+    T[tid * kTLd + tid] = 0.f;
+  }
   __syncthreads();
   MG_CLK(33);
 
@@ -393,18 +526,13 @@ __global__ void __launch_bounds__(kTrsmThreads, 2)
       }
       {
         // T row loaded unconditionally (it does not depend on x, so later steps' loads run ahead
-        // of the substitution chain) and applied by select to the rows still unsolved
+        // of the substitution chain); its entries at or before column i are zero
         const float4 ta = *reinterpret_cast<const float4*>(T + ip * kTLd + ip0);
         const float tv[4] = {ta.x, ta.y, ta.z, ta.w};
 #pragma unroll
-        for (int l = 0; l < kTrsmRows; ++l) {
-          const bool below = part * kTrsmRows + l > i;
+        for (int l = 0; l < kTrsmRows; ++l)
 #pragma unroll
-          for (int q = 0; q < kTrsmCpl; ++q) {
-            const float upd = fmaf(-tv[l], x[q], r[q][l]);
-            r[q][l] = below ? upd : r[q][l];
-          }
-        }
+          for (int q = 0; q < kTrsmCpl; ++q) r[q][l] = fmaf(-tv[l], x[q], r[q][l]);
       }
     }
     __syncwarp();
@@ -495,22 +623,40 @@ int potrf128(float* A, int64_t ld, int64_t j0, int nb, float* t_fwd, float* t_bw
   return cuda_rc();
 }
 
+template <int THREADS>
+static int trsm128_launch(const float* tblock, bool reversed, int nb, const float* B, int64_t ldb,
+                          int64_t ncols, float alpha, float* X, int64_t ldx, __nv_bfloat16* planes,
+                          int64_t ldp, int64_t pstride, __nv_bfloat16* tplanes, int64_t ldtp,
+                          int64_t tpstride, float* colsumsq, cudaStream_t s) {
+  static PerDeviceOnce once;
+  if (int rc = once.run([] {
+        return cudaFuncSetAttribute(trsm128_kernel<THREADS>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(trsm_smem(THREADS)));
+      }))
+    return rc;
+  constexpr int cols = trsm_cols(THREADS);
+  const unsigned grid = static_cast<unsigned>((ncols + cols - 1) / cols);
+  trsm128_kernel<THREADS><<<grid, THREADS, trsm_smem(THREADS), s>>>(
+      tblock, reversed ? 1 : 0, nb, B, ldb, ncols, alpha, X, ldx, planes, ldp, pstride, tplanes, ldtp,
+      tpstride, colsumsq);
+  return cuda_rc();
+}
+
 int trsm128(const float* tblock, bool reversed, int nb, const float* B, int64_t ldb, int64_t ncols,
             float alpha, float* X, int64_t ldx, __nv_bfloat16* planes, int64_t ldp, int64_t pstride,
             __nv_bfloat16* tplanes, int64_t ldtp, int64_t tpstride, float* colsumsq,
             cudaStream_t s) {
   if (ncols <= 0) return 0;
-  static PerDeviceOnce once;
-  if (int rc = once.run([] {
-        return cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(kTrsmSmem));
-      }))
-    return rc;
-  const unsigned grid = static_cast<unsigned>((ncols + kTrsmCols - 1) / kTrsmCols);
-  trsm128_kernel<<<grid, kTrsmThreads, kTrsmSmem, s>>>(tblock, reversed ? 1 : 0, nb, B, ldb, ncols,
-                                                       alpha, X, ldx, planes, ldp, pstride, tplanes,
-                                                       ldtp, tpstride, colsumsq);
-  return cuda_rc();
+  // MG_TRSM_THREADS=256 selects the 8-warp CTAs (A/B measurements)
+  static const bool wide = [] {
+    const char* e = std::getenv("MG_TRSM_THREADS");
+    return e != nullptr && std::atoi(e) == 256;
+  }();
+  return wide ? trsm128_launch<256>(tblock, reversed, nb, B, ldb, ncols, alpha, X, ldx, planes, ldp,
+                                    pstride, tplanes, ldtp, tpstride, colsumsq, s)
+              : trsm128_launch<128>(tblock, reversed, nb, B, ldb, ncols, alpha, X, ldx, planes, ldp,
+                                    pstride, tplanes, ldtp, tpstride, colsumsq, s);
 }
 
 namespace {

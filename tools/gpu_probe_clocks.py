@@ -15,10 +15,15 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 print("rc", raw.mg_debug_clocks(buf))
 v = list(buf)
-print("potrf128: load->sync", v[1]-v[0])
+print("potrf128: global load", v[0]-v[21], " load->sync", v[1]-v[0])
+# stamps of thread 0 (warp 0 = the chain): end of the diagonal block, own block-row solve + wait for
+# warps 1..3, next diagonal block updated (the last sub-panel has neither)
 for kb in range(4):
-    print(f"  kb{kb}: phase1 {v[2+3*kb]-(v[1] if kb==0 else v[4+3*(kb-1)])}  phase2 {v[3+3*kb]-v[2+3*kb]}  phase3 {v[4+3*kb]-v[3+3*kb]}")
-print("  outputs fwd", v[19]-v[13], " bwd", v[20]-v[19], " total", v[20]-v[0])
+    line = f"  kb{kb}: diag {v[2+3*kb]-(v[1] if kb==0 else v[4+3*(kb-1)])}"
+    if kb < 3:
+        line += f"  solve {v[3+3*kb]-v[2+3*kb]}  next-diag update {v[4+3*kb]-v[3+3*kb]}"
+    print(line)
+print("  outputs fwd", v[19]-v[11], " bwd", v[20]-v[19], " total", v[20]-v[0])
 print("trsm128: Tload", v[33]-v[32])
 for rb in range(4):
     prev = v[33] if rb == 0 else v[36+4*(rb-1)]
