@@ -40,6 +40,7 @@ struct Lanes {
   cudaEvent_t misc[2] = {nullptr, nullptr};
   bool serial = true;
   int reserve_sms = 48;   // SMs kept free of persistent bulk CTAs (see LaneScope)
+  bool reserve_from_env = false;   // MG_BULK_RESERVE_SMS given: use it as it is
 
   void record(cudaEvent_t e, cudaStream_t on) const {
     if (!serial) cudaEventRecord(e, on);

@@ -731,7 +731,12 @@ std::atomic<int> g_lane_share{1};
 int Lanes::bulk_cta_cap() const {
   if (serial) return 0;
   const int share = g_lane_share.load(std::memory_order_relaxed);
-  int cap = (device_sm_count() - reserve_sms) / (share < 1 ? 1 : share);
+  // Side by side, the factorisations are bound by their bulk GEMMs on a share of the SMs, not by
+  // one chain: measured with two workers at n = 11008, 16.9 / 17.4 / 17.9 / 18.6 / 20.2 ms per
+  // layer for 16 / 32 / 48 / 64 / 80 reserved SMs (one worker: 19.8 / 19.4 / 19.0 / 19.4 / 20.8);
+  // 8 and 0 are within noise of 16 (profiles/r2_mlp_workers.txt).
+  const int reserve = (share >= 2 && !reserve_from_env && reserve_sms > 16) ? 16 : reserve_sms;
+  int cap = (device_sm_count() - reserve) / (share < 1 ? 1 : share);
   cap &= ~1;                       // CTA pairs
   return cap < 16 ? 16 : cap;
 }
@@ -783,6 +788,7 @@ LaneScope::LaneScope(cudaStream_t user, int64_t n) {
   lanes_.user = user;
   lanes_.serial = false;
   lanes_.reserve_sms = reserve;
+  lanes_.reserve_from_env = reserve_env >= 0;
   cudaEventRecord(lanes_.fork, user);
   cudaStreamWaitEvent(lanes_.chain, lanes_.fork, 0);
   cudaStreamWaitEvent(lanes_.upd, lanes_.fork, 0);
