@@ -260,3 +260,18 @@ def test_layer_streamed_flow_refuses_eager_attention():
         _LayerStepper(adapter, "synthetic")
     model.config._attn_implementation = "sdpa"
     _LayerStepper(adapter, "synthetic")
+
+
+def test_timeline_summary_reads_a_lane_timeline(tmp_path):
+    """tools/timeline_summary.py on a hand-made MG_PROFILE_TIMELINE file: lane totals and the
+    hindsight path (the launch that ends last, then whatever ended closest before each start)."""
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "tl.csv"
+    src.write_text("#rep 0\ncall,old,0x1,0.0,9.0\n#rep 1\n"
+                   "call,potrf,0x1,0.0,1.0\ncall,bulk,0x2,0.5,2.0\ncall,trsm,0x1,2.1,3.0\n")
+    out = tmp_path / "out.txt"
+    subprocess.run([sys.executable, str(root / "tools" / "timeline_summary.py"), str(src), str(out)], check=True)
+    text = out.read_text()
+    assert "3 launches, 3.000 ms" in text            # only the last repetition is read
+    assert "lane 0:    2 launches, busy   1.900 ms" in text
+    assert "hindsight path: 2 launches, 2.400 ms in kernels + 0.100 ms of gaps" in text
